@@ -1,0 +1,305 @@
+// CAAR — compute_and_apply_rhs, one Runge-Kutta stage of the dynamics. Replaces
+// CaarFunctor.{hpp,cpp} / CaarFunctorImpl.hpp of the reference (rsplit > 0 path) plus the small
+// element-wise kernels of prim_driver.cpp / prim_step.cpp / prim_advance_exp.cpp.
+//
+// One thread per (element, level); the 4x4 plane of the level lives in registers, every
+// horizontal operator is thread-local. The three vertical integrals (pressure, hydrostatic
+// geopotential, omega) run in the reference's sequential order through shared memory
+// (non-CUDA branches CaarFunctorImpl.hpp:621-650, :689-729, :854-889), one thread per column.
+// Algorithmic HBM traffic per element and stage: read v,T,dp3d at n0 and nm1 (8 tiles, 4 when
+// nm1 == n0), write 4 tiles, plus read-modify-write of derived_vn0 (2) and omega_p (1) when
+// eta_ave_w != 0.
+#include "hxx.cuh"
+
+HXX_DEFINE_CONSTANTS()
+
+#include "hxx_sphere.cuh"
+
+namespace hxx {
+
+struct CaarArgs {
+  const double* geo;
+  double *v, *t, *dp3d, *vn0, *omega_p, *phi;
+  const double* qdp;
+  int nelem, nm1, n0, np1, n0_qdp;
+  double dt, eta_ave_w;
+  int fold_rsp, store_phi;
+};
+
+template <int E>
+__global__ void __launch_bounds__(E* NLEV, 1) caar_kernel(const CaarArgs a) {
+  constexpr int LS = NLEV + 1;  // odd column stride: conflict-free column walks
+  extern __shared__ double sm[];
+  double* s_p = sm;                  // dp -> pressure
+  double* s_x = sm + E * NPSQ * LS;  // div_vdp -> running sum; then a_k -> phi
+  const int tid = threadIdx.x, e = tid / NLEV, k = tid % NLEV;
+  int ie = blockIdx.x * E + e;
+  const bool valid = ie < a.nelem;
+  if (!valid) ie = a.nelem - 1;
+  const double* __restrict__ g = a.geo + (size_t)ie * NPSQ * GEO_N;
+  const double* v0p = a.v + off_v(ie, a.n0, 0) + k;
+  const double* v1p = a.v + off_v(ie, a.n0, 1) + k;
+  const int col0 = e * NPSQ;
+
+  double dp[NPSQ], div[NPSQ];
+  {
+    double v0[NPSQ], v1[NPSQ];
+    plane_load(a.dp3d + off_s(ie, a.n0) + k, dp);
+    plane_load(v0p, v0);
+    plane_load(v1p, v1);
+    // compute_div_vdp, CaarFunctorImpl.hpp:370-396
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) { v0[p] *= dp[p]; v1[p] *= dp[p]; }
+    if (a.eta_ave_w != 0.0 && valid) {
+      double* n0p = a.vn0 + ((size_t)ie * 2 + 0) * NLF + k;
+      double* n1p = a.vn0 + ((size_t)ie * 2 + 1) * NLF + k;
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) {
+        n0p[p * NLEV] += a.eta_ave_w * v0[p];
+        n1p[p * NLEV] += a.eta_ave_w * v1[p];
+      }
+    }
+    divergence_sphere(g, v0, v1, div);
+  }
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) {
+    s_p[(col0 + p) * LS + k] = dp[p];
+    s_x[(col0 + p) * LS + k] = div[p];
+  }
+  __syncthreads();
+  if (tid < E * NPSQ) {
+    // compute_pressure (:621-650) and the omega running sum (:854-889), two independent chains
+    double* cp_ = s_p + tid * LS;
+    double* cx = s_x + tid * LS;
+    double dp_prev = 0.0, p_prev = dc.hyai0 * dc.ps0, integ = 0.0;
+#pragma unroll 8
+    for (int kk = 0; kk < NLEV; ++kk) {
+      const double d = cp_[kk];
+      const double pk = p_prev + 0.5 * (dp_prev + d);
+      cp_[kk] = pk;
+      p_prev = pk;
+      dp_prev = d;
+      const double dv = cx[kk];
+      cx[kk] = integ;
+      integ = integ + dv;
+    }
+  }
+  __syncthreads();
+
+  double pr[NPSQ], tv[NPSQ], tn0[NPSQ];
+  plane_load(a.t + off_s(ie, a.n0) + k, tn0);
+  if (a.n0_qdp < 0) {  // :333-344
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) tv[p] = tn0[p];
+  } else {  // :348-363
+    const double* q = a.qdp + off_q(ie, a.n0_qdp, 0) + k;
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) {
+      double Qt = q[p * NLEV] / dp[p];
+      Qt *= (Rwater_vapor / Rgas - 1.0);
+      Qt += 1.0;
+      tv[p] = tn0[p] * Qt;
+    }
+  }
+  double sint[NPSQ];  // integration + 0.5*div_vdp of preq_omega_ps
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) {
+    const int slot = (col0 + p) * LS + k;
+    pr[p] = s_p[slot];
+    sint[p] = s_x[slot] + 0.5 * div[p];
+    s_x[slot] = Rgas * tv[p] * (dp[p] * 0.5 / pr[p]);  // preq_hydrostatic :689-729
+  }
+  // compute_dp3d_np1 :468-493 (eta_dot_dpdn == 0 for rsplit > 0); stored now, dp/div die here
+  if (valid) {
+    const double* dm = a.dp3d + off_s(ie, a.nm1) + k;
+    double* dn = a.dp3d + off_s(ie, a.np1) + k;
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) {
+      double r = geo_ld(g, p, G_SPHEREMP) * (dm[p * NLEV] - div[p] * a.dt);
+      if (a.fold_rsp && is_interior_pt(p)) r *= geo_ld(g, p, G_RSPHEREMP);
+      dn[p * NLEV] = r;
+    }
+  }
+  __syncthreads();
+  if (tid < E * NPSQ) {
+    double* cx = s_x + tid * LS;
+    const int iec = min(blockIdx.x * E + tid / NPSQ, a.nelem - 1);
+    const double phis = a.geo[((size_t)iec * NPSQ + (tid % NPSQ)) * GEO_N + G_PHIS];
+    double integ = 0.0;
+#pragma unroll 8
+    for (int kk = NLEV - 1; kk >= 0; --kk) {
+      const double ak = cx[kk];
+      cx[kk] = phis + 2.0 * integ + ak;
+      integ = integ + ak;
+    }
+  }
+  __syncthreads();
+
+  double v0[NPSQ], v1[NPSQ], omega[NPSQ], g0[NPSQ], g1[NPSQ];
+  plane_load(v0p, v0);
+  plane_load(v1p, v1);
+  gradient_sphere(g, pr, g0, g1);  // grad p
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) {
+    const double vgrad_p = v0[p] * g0[p] + v1[p] * g1[p];
+    omega[p] = (vgrad_p - sint[p]) / pr[p];
+  }
+  if (a.eta_ave_w != 0.0 && valid) {  // compute_omega_p :412-423
+    double* om = a.omega_p + off_f(ie) + k;
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) om[p * NLEV] += a.eta_ave_w * omega[p];
+  }
+  {  // compute_temperature_np1 :430-463
+    double tg0[NPSQ], tg1[NPSQ];
+    gradient_sphere(g, tn0, tg0, tg1);
+    const double* tm = a.t + off_s(ie, a.nm1) + k;
+    double* tp = a.t + off_s(ie, a.np1) + k;
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) {
+      const double vgrad_t = v0[p] * tg0[p] + v1[p] * tg1[p];
+      const double ttens = -vgrad_t + kappa * tv[p] * omega[p];
+      double r = ttens * a.dt + tm[p * NLEV];
+      r *= geo_ld(g, p, G_SPHEREMP);
+      if (a.fold_rsp && is_interior_pt(p)) r *= geo_ld(g, p, G_RSPHEREMP);
+      if (valid) tp[p * NLEV] = r;
+    }
+  }
+  // compute_velocity_np1 :184-232 with compute_energy_grad :98-132
+  {
+    double ephi[NPSQ];
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) {
+      const double r = Rgas * (tv[p] / pr[p]);
+      g0[p] = r * g0[p];
+      g1[p] = r * g1[p];
+      const double phi = s_x[(col0 + p) * LS + k];
+      if (a.store_phi && valid) a.phi[off_f(ie) + p * NLEV + k] = phi;
+      ephi[p] = 0.5 * (v0[p] * v0[p] + v1[p] * v1[p]) + phi;
+    }
+    gradient_sphere_update(g, ephi, g0, g1);
+  }
+  {
+    double vort[NPSQ];
+    vorticity_sphere(g, v0, v1, vort);
+    const double* vm0 = a.v + off_v(ie, a.nm1, 0) + k;
+    const double* vm1 = a.v + off_v(ie, a.nm1, 1) + k;
+    double* vp0 = a.v + off_v(ie, a.np1, 0) + k;
+    double* vp1 = a.v + off_v(ie, a.np1, 1) + k;
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) {
+      const double vt = vort[p] + geo_ld(g, p, G_FCOR);
+      double e0 = -g0[p] + v1[p] * vt;
+      double e1 = -g1[p] - v0[p] * vt;
+      e0 = e0 * a.dt + vm0[p * NLEV];
+      e1 = e1 * a.dt + vm1[p * NLEV];
+      const double sm_ = geo_ld(g, p, G_SPHEREMP);
+      e0 = sm_ * e0;
+      e1 = sm_ * e1;
+      if (a.fold_rsp && is_interior_pt(p)) {
+        const double rs = geo_ld(g, p, G_RSPHEREMP);
+        e0 *= rs;
+        e1 *= rs;
+      }
+      if (valid) {
+        vp0[p * NLEV] = e0;
+        vp1[p * NLEV] = e1;
+      }
+    }
+  }
+}
+
+void caar_run(int nm1, int n0, int np1, double dt, double eta_ave_w, int n0_qdp, bool with_dss) {
+  if (!S.nelemd) return;
+  CaarArgs a{S.geo, S.v, S.t, S.dp3d, S.derived_vn0, S.omega_p, S.phi, S.qdp, S.nelemd, nm1, n0, np1, n0_qdp,
+             dt, eta_ave_w, with_dss ? 1 : 0, S.store_phi ? 1 : 0};
+  constexpr size_t smem = 2 * (size_t)EPB * NPSQ * (NLEV + 1) * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    CUDA_OK(cudaFuncSetAttribute(caar_kernel<EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  caar_kernel<EPB><<<nblocks_elem(S.nelemd), EPB * NLEV, smem, S.stream>>>(a);
+  KERNEL_LAUNCHED();
+  if (with_dss) dss_exchange(fields_caar(np1), true);  // CaarFunctor.cpp:113
+}
+
+// ---- element-wise kernels -----------------------------------------------------------------
+// prim_advance_exp.cpp:143-154 : u(nm1) = (5 u(nm1) - u(n0)) / 4 for v (2 tiles), T, dp3d
+__global__ void rk_combine_kernel(double* __restrict__ v, double* __restrict__ t, double* __restrict__ dp, int nm1,
+                                  int n0) {
+  const int ie = blockIdx.x;
+  double* vm = v + off_v(ie, nm1, 0);
+  const double* vn = v + off_v(ie, n0, 0);
+  double* tm = t + off_s(ie, nm1);
+  const double* tn = t + off_s(ie, n0);
+  double* dm = dp + off_s(ie, nm1);
+  const double* dn = dp + off_s(ie, n0);
+  for (int i = threadIdx.x; i < 2 * NLF; i += blockDim.x) vm[i] = (5.0 * vm[i] - vn[i]) / 4.0;
+  for (int i = threadIdx.x; i < NLF; i += blockDim.x) {
+    tm[i] = (5.0 * tm[i] - tn[i]) / 4.0;
+    dm[i] = (5.0 * dm[i] - dn[i]) / 4.0;
+  }
+}
+void rk_combine(int nm1, int n0) {
+  if (!S.nelemd) return;
+  rk_combine_kernel<<<S.nelemd, 288, 0, S.stream>>>(S.v, S.t, S.dp3d, nm1, n0);
+  KERNEL_LAUNCHED();
+}
+
+// prim_driver.cpp:98-111
+__global__ void dp3d_from_ps_kernel(double* __restrict__ dp3d, const double* __restrict__ ps_v, int n0) {
+  const int ie = blockIdx.x;
+  double* dp = dp3d + off_s(ie, n0);
+  const double* ps = ps_v + ((size_t)ie * NTL + n0) * NPSQ;
+  for (int i = threadIdx.x; i < NLF; i += blockDim.x) {
+    const int p = i / NLEV, k = i % NLEV;
+    dp[i] = dc.dai[k] * dc.ps0 + dc.dbi[k] * ps[p];
+  }
+}
+void dp3d_from_ps(int n0) {
+  if (!S.nelemd) return;
+  dp3d_from_ps_kernel<<<S.nelemd, 288, 0, S.stream>>>(S.dp3d, S.ps_v, n0);
+  KERNEL_LAUNCHED();
+}
+
+// prim_step.cpp:51-66
+__global__ void derived_dp_kernel(double* __restrict__ derived_dp, const double* __restrict__ dp3d, int n0) {
+  const int ie = blockIdx.x;
+  const double* s = dp3d + off_s(ie, n0);
+  double* d = derived_dp + off_f(ie);
+  for (int i = threadIdx.x; i < NLF; i += blockDim.x) d[i] = s[i];
+}
+void prim_step_init(int n0) {
+  if (!S.nelemd) return;
+  const size_t f3 = (size_t)S.nelemd * NLF * sizeof(double);
+  CUDA_OK(cudaMemsetAsync(S.eta_dot_dpdn, 0, f3, S.stream));
+  CUDA_OK(cudaMemsetAsync(S.derived_vn0, 0, 2 * f3, S.stream));
+  CUDA_OK(cudaMemsetAsync(S.omega_p, 0, f3, S.stream));
+  if (S.p.nu_p > 0) {
+    CUDA_OK(cudaMemsetAsync(S.dpdiss_ave, 0, f3, S.stream));
+    CUDA_OK(cudaMemsetAsync(S.dpdiss_biharmonic, 0, f3, S.stream));
+  }
+  derived_dp_kernel<<<S.nelemd, 288, 0, S.stream>>>(S.derived_dp, S.dp3d, n0);
+  KERNEL_LAUNCHED();
+}
+
+// prim_driver.cpp:171-206
+__global__ void update_q_kernel(double* __restrict__ Q, const double* __restrict__ qdp, const double* __restrict__ ps_v,
+                                int np1_qdp, int np1) {
+  const int ie = blockIdx.x, q = blockIdx.y;
+  const double* qd = qdp + off_q(ie, np1_qdp, q);
+  double* out = Q + ((size_t)ie * QSIZE_D + q) * NLF;
+  const double* ps = ps_v + ((size_t)ie * NTL + np1) * NPSQ;
+  for (int i = threadIdx.x; i < NLF; i += blockDim.x) {
+    const int p = i / NLEV, k = i % NLEV;
+    const double dp = dc.dai[k] * dc.ps0 + dc.dbi[k] * ps[p];
+    out[i] = qd[i] / dp;
+  }
+}
+void update_q(int np1_qdp, int np1) {
+  if (!S.nelemd || !S.p.qsize) return;
+  update_q_kernel<<<dim3(S.nelemd, S.p.qsize), 288, 0, S.stream>>>(S.Q, S.qdp, S.ps_v, np1_qdp, np1);
+  KERNEL_LAUNCHED();
+}
+
+}  // namespace hxx

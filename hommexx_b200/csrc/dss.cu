@@ -1,0 +1,408 @@
+// Boundary exchange (DSS) — replaces mpi/BoundaryExchange.{hpp,cpp}, BuffersManager and
+// Connectivity of the reference.
+//
+// Design (not the reference's pack -> buffer -> unpack): the exchange is NODE-CENTRIC. At
+// init_boundary_exchanges_c the 8-neighbour connection list is turned into one record per
+// unique GLL boundary node (2 sharers on an edge, 4 at an element corner, 3 at a cube vertex).
+// One thread handles (node, level): it loads each member's value once, forms for every local
+// member the sum in the reference's unpack order (own value, then edges S,N,W,E for k=0..3,
+// then corners — BoundaryExchange.cpp:512-524, so results are bit-identical), applies
+// rspheremp and stores. Traffic: 12/16 of a field read + 12/16 written, no staging buffers for
+// on-rank neighbours (the reference's `local_buffer`, BoundaryExchange.cpp:327, disappears).
+// Interior points never take part; when rspheremp is requested their scaling is folded into
+// the producing kernel. Members owned by another rank arrive through a halo buffer filled by a
+// pack kernel + grouped ncclSend/ncclRecv over NVLink (one message per neighbour rank, slot
+// order agreed by sorting connections on (owner gid, owner pos), cf. BoundaryExchange.cpp:1050).
+#include <algorithm>
+#include <array>
+#include <map>
+#include <tuple>
+#include <unordered_map>
+
+#include "hxx.cuh"
+#ifdef HXX_WITH_NCCL
+#include <nccl.h>
+#endif
+
+namespace hxx {
+
+// ConnectivityHelpers.hpp:145-176
+static const int EDGE_PTS[4][4] = {{0, 1, 2, 3}, {12, 13, 14, 15}, {0, 4, 8, 12}, {3, 7, 11, 15}};
+static const int CORNER_PTS[4] = {0, 3, 12, 15};
+
+constexpr int NODES_PB = (NLEV * 4 <= 288) ? 4 : 2;  // nodes per block
+constexpr int DSS_FPB = 8;                           // fields per thread (grid.y chunks)
+
+template <bool RSP>
+__global__ void __launch_bounds__(NODES_PB* NLEV)
+    dss_nodes_kernel(const DssNode* __restrict__ nodes, int nnodes, FieldList fl, const double* __restrict__ geo,
+                     const double* __restrict__ halo) {
+  const int nl = threadIdx.x / NLEV, k = threadIdx.x % NLEV;
+  const int node = blockIdx.x * NODES_PB + nl;
+  if (node >= nnodes) return;
+  const DssNode nd = nodes[node];
+  double rs[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+    rs[m] = (RSP && m < nd.nmem && nd.src[m] >= 0) ? __ldg(geo + (size_t)nd.src[m] * GEO_N + G_RSPHEREMP) : 1.0;
+  const int f0 = blockIdx.y * DSS_FPB, f1 = min(fl.nf, f0 + DSS_FPB);
+  for (int f = f0; f < f1; ++f) {
+    double* base = fl.base[f];
+    const long long es = fl.estride[f];
+    double val[4];
+    double* ptr[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      val[m] = 0.0;
+      ptr[m] = nullptr;
+      if (m < nd.nmem) {
+        const int s = nd.src[m];
+        if (s >= 0) {
+          ptr[m] = base + (size_t)(s >> 4) * es + (s & 15) * NLEV + k;
+          val[m] = *ptr[m];
+        } else {
+          val[m] = halo[((size_t)(~s) * fl.nf + f) * NLEV + k];
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      if (ptr[m]) {
+        double acc = val[m];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const int o = nd.ord[m][t];
+          if (o < 4) acc += val[o];
+        }
+        if (RSP) acc *= rs[m];
+        *ptr[m] = acc;
+      }
+    }
+  }
+}
+
+__global__ void scale_interior_kernel(FieldList fl, const double* __restrict__ geo, int nelem) {
+  const int ie = blockIdx.x, f = blockIdx.y;
+  if (ie >= nelem) return;
+  double* fld = fl.base[f] + (size_t)ie * fl.estride[f];
+  for (int i = threadIdx.x; i < 4 * NLEV; i += blockDim.x) {
+    const int ip = i / NLEV, k = i % NLEV;
+    const int p = ip == 0 ? 5 : ip == 1 ? 6 : ip == 2 ? 9 : 10;
+    fld[p * NLEV + k] *= geo[((size_t)ie * NPSQ + p) * GEO_N + G_RSPHEREMP];
+  }
+}
+
+// send buffer [pt][field][lev]
+__global__ void halo_pack_kernel(const int* __restrict__ send_src, int npts, FieldList fl, double* __restrict__ buf) {
+  const int i = blockIdx.x, f = blockIdx.y;
+  const int s = send_src[i];
+  const double* src = fl.base[f] + (size_t)(s >> 4) * fl.estride[f] + (s & 15) * NLEV;
+  double* dst = buf + ((size_t)i * fl.nf + f) * NLEV;
+  for (int k = threadIdx.x; k < NLEV; k += blockDim.x) dst[k] = src[k];
+}
+
+// min/max: qlim [ie][QSIZE_D][2][NLEV]; halo slot [conn][qsize][2][NLEV]
+__global__ void minmax_pack_kernel(const int* __restrict__ send_elem, const double* __restrict__ qlim, int qsize,
+                                   double* __restrict__ buf) {
+  const int i = blockIdx.x, q = blockIdx.y;
+  const double* src = qlim + ((size_t)send_elem[i] * QSIZE_D + q) * 2 * NLEV;
+  double* dst = buf + ((size_t)i * qsize + q) * 2 * NLEV;
+  for (int k = threadIdx.x; k < 2 * NLEV; k += blockDim.x) dst[k] = src[k];
+}
+
+__global__ void minmax_kernel(const int* __restrict__ nbr8, const double* __restrict__ qin, double* __restrict__ qout,
+                              const double* __restrict__ halo, int qsize) {
+  const int ie = blockIdx.x, q = blockIdx.y;
+  for (int k = threadIdx.x; k < NLEV; k += blockDim.x) {
+    const double* mine = qin + ((size_t)ie * QSIZE_D + q) * 2 * NLEV;
+    double mn = mine[k], mx = mine[NLEV + k];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int nb = nbr8[ie * 8 + c];
+      if (nb == DSS_NONE) continue;
+      const double* th = nb >= 0 ? qin + ((size_t)nb * QSIZE_D + q) * 2 * NLEV
+                                 : halo + ((size_t)(~nb) * qsize + q) * 2 * NLEV;
+      mn = fmin(mn, th[k]);
+      mx = fmax(mx, th[NLEV + k]);
+    }
+    double* o = qout + ((size_t)ie * QSIZE_D + q) * 2 * NLEV;
+    o[k] = mn;
+    o[NLEV + k] = mx;
+  }
+}
+
+// ---- plan ---------------------------------------------------------------------------------
+namespace {
+struct UF {
+  std::vector<int> parent;
+  int find(int x) { while (parent[x] != x) x = parent[x] = parent[parent[x]]; return x; }
+  void unite(int a, int b) { a = find(a); b = find(b); if (a != b) parent[std::max(a, b)] = std::min(a, b); }
+};
+}  // namespace
+
+void free_exchange_plan() {
+  if (S.nodes) { cudaFree(S.nodes); S.nodes = nullptr; }
+  if (S.nbr8) { cudaFree(S.nbr8); S.nbr8 = nullptr; }
+  if (S.send_src) { cudaFree(S.send_src); S.send_src = nullptr; }
+  if (S.send_conn_elem) { cudaFree(S.send_conn_elem); S.send_conn_elem = nullptr; }
+  if (S.sendbuf) { cudaFree(S.sendbuf); S.sendbuf = nullptr; }
+  if (S.recvbuf) { cudaFree(S.recvbuf); S.recvbuf = nullptr; }
+  S.nnodes = 0; S.n_halo_pts = S.n_send_pts = S.n_halo_conn = S.n_send_conn = 0;
+  S.peer.clear();
+}
+
+void build_exchange_plan() {
+  free_exchange_plan();
+  const int n = S.nelemd;
+  // -- remote connections: send order (l_gid, l_pos), receive order (r_gid, r_pos), per peer
+  struct RC { int peer, gid, pos, ie, c; };
+  std::vector<RC> snd, rcv;
+  for (int ie = 0; ie < n; ++ie)
+    for (int c = 0; c < 8; ++c) {
+      const ConnInfo& i = S.conn[(size_t)ie * 8 + c];
+      if (i.kind == 2 || i.sharing != 1) continue;
+      snd.push_back({i.remote_pid, i.l_gid, i.l_pos, ie, c});
+      rcv.push_back({i.remote_pid, i.r_gid, i.r_pos, ie, c});
+    }
+  auto cmp = [](const RC& a, const RC& b) { return std::tie(a.peer, a.gid, a.pos) < std::tie(b.peer, b.gid, b.pos); };
+  std::sort(snd.begin(), snd.end(), cmp);
+  std::sort(rcv.begin(), rcv.end(), cmp);
+  std::vector<int> send_src, send_conn_elem;
+  std::map<int, std::array<int, 8>> per;  // peer -> {send_off,send_cnt,recv_off,recv_cnt, csend_off,csend_cnt,crecv_off,crecv_cnt}
+  for (size_t j = 0; j < snd.size(); ++j) {
+    const RC& r = snd[j];
+    auto& a = per.try_emplace(r.peer, std::array<int, 8>{-1, 0, -1, 0, -1, 0, -1, 0}).first->second;
+    if (a[0] < 0) { a[0] = (int)send_src.size(); a[4] = (int)j; }
+    if (r.c < 4) for (int k = 0; k < 4; ++k) send_src.push_back(r.ie * 16 + EDGE_PTS[r.c][k]);
+    else send_src.push_back(r.ie * 16 + CORNER_PTS[r.c - 4]);
+    a[1] = (int)send_src.size() - a[0];
+    a[5] = (int)j + 1 - a[4];
+    send_conn_elem.push_back(r.ie);
+  }
+  std::unordered_map<long long, int> halo_of;  // remote (gid*16+pt) -> halo point index
+  std::vector<int> halo_conn_of((size_t)n * 8, -1);
+  int nh = 0;
+  for (size_t j = 0; j < rcv.size(); ++j) {
+    const RC& r = rcv[j];
+    auto& a = per.try_emplace(r.peer, std::array<int, 8>{-1, 0, -1, 0, -1, 0, -1, 0}).first->second;
+    if (a[2] < 0) { a[2] = nh; a[6] = (int)j; }
+    if (r.pos < 4) for (int k = 0; k < 4; ++k) halo_of.emplace((long long)r.gid * 16 + EDGE_PTS[r.pos][k], nh++);
+    else halo_of.emplace((long long)r.gid * 16 + CORNER_PTS[r.pos - 4], nh++);
+    a[3] = nh - a[2];
+    a[7] = (int)j + 1 - a[6];
+    halo_conn_of[(size_t)r.ie * 8 + r.c] = (int)j;
+  }
+  // note: emplace keeps the first index of a repeated remote point, but nh advanced for every
+  // slot point, so the buffer layout stays the plain concatenation of the slots.
+  S.n_send_pts = (int)send_src.size(); S.n_halo_pts = nh;
+  S.n_send_conn = (int)snd.size(); S.n_halo_conn = (int)rcv.size();
+  for (auto& kv : per) {
+    S.peer.push_back(kv.first);
+    S.peer_send_off.push_back(kv.second[0]); S.peer_send_cnt.push_back(kv.second[1]);
+    S.peer_recv_off.push_back(kv.second[2]); S.peer_recv_cnt.push_back(kv.second[3]);
+    S.peer_csend_off.push_back(kv.second[4]); S.peer_csend_cnt.push_back(kv.second[5]);
+    S.peer_crecv_off.push_back(kv.second[6]); S.peer_crecv_cnt.push_back(kv.second[7]);
+    if (kv.second[1] != kv.second[3] || kv.second[5] != kv.second[7])
+      runtime_abort("build_exchange_plan: asymmetric connections with a neighbour rank", 13);
+  }
+
+  // -- ordered contributions per local boundary point, and node grouping
+  struct Src { long long key; int local; };  // local: lid*16+pt or -1
+  std::vector<std::vector<Src>> contrib((size_t)n * 16);
+  std::unordered_map<long long, int> id_of;  // member key -> dense id
+  std::vector<long long> key_of;
+  std::vector<int> local_of;
+  auto member = [&](long long key, int local) {
+    auto it = id_of.find(key);
+    if (it != id_of.end()) { if (local >= 0) local_of[it->second] = local; return it->second; }
+    const int id = (int)key_of.size();
+    id_of.emplace(key, id); key_of.push_back(key); local_of.push_back(local);
+    return id;
+  };
+  auto gid_of_local = [&](int ie) {
+    for (int c = 0; c < 8; ++c) if (S.conn[(size_t)ie * 8 + c].kind != 2) return S.conn[(size_t)ie * 8 + c].l_gid;
+    return -1 - ie;  // isolated element (unit-test sessions): private key space
+  };
+  UF uf;
+  std::vector<int> self_id((size_t)n * 16, -1);
+  auto key = [](int gid, int pt) { return (long long)gid * 16 + pt; };
+  for (int ie = 0; ie < n; ++ie) {
+    const int gid = gid_of_local(ie);
+    auto add = [&](int pt, const ConnInfo& i, int rpt) {
+      const bool loc = i.sharing == 0;
+      contrib[(size_t)ie * 16 + pt].push_back({key(i.r_gid, rpt), loc ? i.r_lid * 16 + rpt : -1});
+    };
+    for (int k = 0; k < 4; ++k)
+      for (int ed = 0; ed < 4; ++ed) {
+        const ConnInfo& i = S.conn[(size_t)ie * 8 + ed];
+        if (i.kind == 2) continue;
+        add(EDGE_PTS[ed][k], i, EDGE_PTS[i.r_pos][i.direction ? 3 - k : k]);
+      }
+    for (int c = 0; c < 4; ++c) {
+      const ConnInfo& i = S.conn[(size_t)ie * 8 + 4 + c];
+      if (i.kind == 2) continue;
+      add(CORNER_PTS[c], i, CORNER_PTS[i.r_pos - 4]);
+    }
+    for (int pt = 0; pt < 16; ++pt) {
+      if (contrib[(size_t)ie * 16 + pt].empty()) continue;
+      self_id[(size_t)ie * 16 + pt] = member(key(gid, pt), ie * 16 + pt);
+    }
+  }
+  for (size_t lp = 0; lp < contrib.size(); ++lp)
+    for (const Src& s : contrib[lp]) member(s.key, s.local);
+  uf.parent.resize(key_of.size());
+  for (size_t i = 0; i < uf.parent.size(); ++i) uf.parent[i] = (int)i;
+  for (size_t lp = 0; lp < contrib.size(); ++lp)
+    for (const Src& s : contrib[lp]) uf.unite(self_id[lp], id_of[s.key]);
+  std::unordered_map<int, int> node_of_root;
+  std::vector<DssNode> nodes;
+  std::vector<std::vector<int>> node_members;
+  for (size_t i = 0; i < key_of.size(); ++i) {
+    const int r = uf.find((int)i);
+    auto it = node_of_root.find(r);
+    int nid;
+    if (it == node_of_root.end()) {
+      nid = (int)nodes.size();
+      node_of_root.emplace(r, nid);
+      DssNode nd;
+      for (int m = 0; m < 4; ++m) { nd.src[m] = DSS_NONE; for (int t = 0; t < 3; ++t) nd.ord[m][t] = 255; }
+      nd.nmem = 0; nd.pad[0] = nd.pad[1] = nd.pad[2] = 0;
+      nodes.push_back(nd);
+      node_members.emplace_back();
+    } else nid = it->second;
+    if (nodes[nid].nmem >= 4) runtime_abort("build_exchange_plan: a GLL node has more than 4 sharers", 13);
+    const int m = nodes[nid].nmem++;
+    node_members[nid].push_back((int)i);
+    if (local_of[i] >= 0) nodes[nid].src[m] = local_of[i];
+    else {
+      auto h = halo_of.find(key_of[i]);
+      if (h == halo_of.end()) runtime_abort("build_exchange_plan: remote GLL point without a halo slot", 13);
+      nodes[nid].src[m] = ~h->second;
+    }
+  }
+  for (size_t lp = 0; lp < contrib.size(); ++lp) {
+    if (contrib[lp].empty()) continue;
+    const int nid = node_of_root[uf.find(self_id[lp])];
+    const auto& mem = node_members[nid];
+    const int me = (int)(std::find(mem.begin(), mem.end(), self_id[lp]) - mem.begin());
+    if (contrib[lp].size() > 3) runtime_abort("build_exchange_plan: more than 3 contributions to a point", 13);
+    for (size_t t = 0; t < contrib[lp].size(); ++t) {
+      const int id = id_of[contrib[lp][t].key];
+      nodes[nid].ord[me][t] = (uint8_t)(std::find(mem.begin(), mem.end(), id) - mem.begin());
+    }
+  }
+  S.nnodes = (int)nodes.size();
+  if (S.nnodes) {
+    CUDA_OK(cudaMalloc(&S.nodes, nodes.size() * sizeof(DssNode)));
+    CUDA_OK(cudaMemcpy(S.nodes, nodes.data(), nodes.size() * sizeof(DssNode), cudaMemcpyHostToDevice));
+  }
+  // -- neighbour table for the min/max exchange
+  std::vector<int> nbr8((size_t)n * 8, DSS_NONE);
+  for (int ie = 0; ie < n; ++ie)
+    for (int c = 0; c < 8; ++c) {
+      const ConnInfo& i = S.conn[(size_t)ie * 8 + c];
+      if (i.kind == 2) continue;
+      nbr8[(size_t)ie * 8 + c] = i.sharing == 0 ? i.r_lid : ~halo_conn_of[(size_t)ie * 8 + c];
+    }
+  CUDA_OK(cudaMalloc(&S.nbr8, std::max<size_t>(1, nbr8.size()) * sizeof(int)));
+  if (n) CUDA_OK(cudaMemcpy(S.nbr8, nbr8.data(), nbr8.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (S.n_send_pts) {
+    CUDA_OK(cudaMalloc(&S.send_src, send_src.size() * sizeof(int)));
+    CUDA_OK(cudaMemcpy(S.send_src, send_src.data(), send_src.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&S.send_conn_elem, send_conn_elem.size() * sizeof(int)));
+    CUDA_OK(cudaMemcpy(S.send_conn_elem, send_conn_elem.data(), send_conn_elem.size() * sizeof(int), cudaMemcpyHostToDevice));
+    const size_t nd = std::max((size_t)S.n_send_pts * MAX_DSS_FIELDS * NLEV, (size_t)S.n_send_conn * QSIZE_D * 2 * NLEV);
+    CUDA_OK(cudaMalloc(&S.sendbuf, nd * sizeof(double)));
+    CUDA_OK(cudaMalloc(&S.recvbuf, nd * sizeof(double)));
+  }
+}
+
+// grouped send/recv with every neighbour rank; offsets/counts in units of `unit` doubles
+static void halo_sendrecv(const std::vector<int>& soff, const std::vector<int>& scnt, const std::vector<int>& roff,
+                          const std::vector<int>& rcnt, size_t unit) {
+#ifdef HXX_WITH_NCCL
+  ncclComm_t comm = (ncclComm_t)S.nccl;
+  if (!comm) runtime_abort("halo exchange: NCCL communicator not initialised", 13);
+  ncclGroupStart();
+  for (size_t i = 0; i < S.peer.size(); ++i) {
+    ncclSend(S.sendbuf + (size_t)soff[i] * unit, (size_t)scnt[i] * unit, ncclDouble, S.peer[i], comm, S.stream);
+    ncclRecv(S.recvbuf + (size_t)roff[i] * unit, (size_t)rcnt[i] * unit, ncclDouble, S.peer[i], comm, S.stream);
+  }
+  if (ncclGroupEnd() != ncclSuccess) runtime_abort("halo exchange: ncclGroupEnd failed", 1);
+#else
+  (void)soff; (void)scnt; (void)roff; (void)rcnt; (void)unit;
+  runtime_abort("halo exchange: built without NCCL", 12);
+#endif
+}
+
+void dss_exchange(const FieldList& fl, bool rspheremp) {
+  if (S.n_send_pts) {
+    halo_pack_kernel<<<dim3(S.n_send_pts, fl.nf), 96, 0, S.stream>>>(S.send_src, S.n_send_pts, fl, S.sendbuf);
+    KERNEL_LAUNCHED();
+    halo_sendrecv(S.peer_send_off, S.peer_send_cnt, S.peer_recv_off, S.peer_recv_cnt, (size_t)fl.nf * NLEV);
+  }
+  if (!S.nnodes) return;
+  const dim3 grid((S.nnodes + NODES_PB - 1) / NODES_PB, (fl.nf + DSS_FPB - 1) / DSS_FPB);
+  if (rspheremp) dss_nodes_kernel<true><<<grid, NODES_PB * NLEV, 0, S.stream>>>(S.nodes, S.nnodes, fl, S.geo, S.recvbuf);
+  else dss_nodes_kernel<false><<<grid, NODES_PB * NLEV, 0, S.stream>>>(S.nodes, S.nnodes, fl, S.geo, S.recvbuf);
+  KERNEL_LAUNCHED();
+}
+
+void scale_interior_rspheremp(const FieldList& fl) {
+  if (!S.nelemd) return;
+  scale_interior_kernel<<<dim3(S.nelemd, fl.nf), 96, 0, S.stream>>>(fl, S.geo, S.nelemd);
+  KERNEL_LAUNCHED();
+}
+
+void minmax_exchange() {
+  const int nq = S.p.qsize;
+  if (!S.nelemd || !nq) return;
+  if (S.n_send_conn) {
+    minmax_pack_kernel<<<dim3(S.n_send_conn, nq), 96, 0, S.stream>>>(S.send_conn_elem, S.qlim, nq, S.sendbuf);
+    KERNEL_LAUNCHED();
+    halo_sendrecv(S.peer_csend_off, S.peer_csend_cnt, S.peer_crecv_off, S.peer_crecv_cnt, (size_t)nq * 2 * NLEV);
+  }
+  minmax_kernel<<<dim3(S.nelemd, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, S.recvbuf, nq);
+  KERNEL_LAUNCHED();
+  std::swap(S.qlim, S.qlim_x);
+}
+
+// ---- registered field sets (the reference's register_field calls) -------------------------
+FieldList fields_caar(int tl) {  // CaarFunctorImpl.hpp:68-79
+  FieldList f;
+  f.nf = 4;
+  f.base[0] = S.v + off_v(0, tl, 0); f.estride[0] = (long long)NTL * 2 * NLF;
+  f.base[1] = S.v + off_v(0, tl, 1); f.estride[1] = (long long)NTL * 2 * NLF;
+  f.base[2] = S.t + off_s(0, tl); f.estride[2] = (long long)NTL * NLF;
+  f.base[3] = S.dp3d + off_s(0, tl); f.estride[3] = (long long)NTL * NLF;
+  return f;
+}
+FieldList fields_hv() {  // HyperviscosityFunctorImpl.cpp:44-54
+  FieldList f;
+  f.nf = 4;
+  f.base[0] = S.vtens; f.estride[0] = 2 * NLF;
+  f.base[1] = S.vtens + NLF; f.estride[1] = 2 * NLF;
+  f.base[2] = S.ttens; f.estride[2] = NLF;
+  f.base[3] = S.dptens; f.estride[3] = NLF;
+  return f;
+}
+double* dss_var(int dss_opt) {
+  return dss_opt == DSS_ETA ? S.eta_dot_dpdn : dss_opt == DSS_OMEGA ? S.omega_p : S.divdp_proj;
+}
+FieldList fields_euler(int tq, int dss_opt) {  // EulerStepFunctorImpl.hpp:137-153
+  FieldList f;
+  const int nq = S.p.qsize;
+  f.nf = nq + 1;
+  for (int q = 0; q < nq; ++q) { f.base[q] = S.qdp + off_q(0, tq, q); f.estride[q] = (long long)QNTL * QSIZE_D * NLF; }
+  f.base[nq] = dss_var(dss_opt); f.estride[nq] = NLF;
+  return f;
+}
+FieldList fields_qtens() {  // EulerStepFunctorImpl.hpp:155-161
+  FieldList f;
+  const int nq = S.p.qsize;
+  f.nf = nq;
+  for (int q = 0; q < nq; ++q) { f.base[q] = S.qtens_biharmonic + (size_t)q * NLF; f.estride[q] = (long long)QSIZE_D * NLF; }
+  return f;
+}
+
+}  // namespace hxx

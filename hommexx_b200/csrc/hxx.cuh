@@ -1,0 +1,209 @@
+// hommexx_b200 — common declarations of the B200-native preqx dycore (sm_100a, FP64).
+//
+// Data layout in HBM (level index innermost, as the reference's device views,
+// src/share/cxx/Elements.hpp:44-48 / Types.hpp:76):
+//   v    [ie][3][2][16][NLEV]   t, dp3d [ie][3][16][NLEV]   ps_v [ie][3][16]
+//   qdp  [ie][2][QSIZE_D][16][NLEV]   Q, qtens_biharmonic [ie][QSIZE_D][16][NLEV]
+//   qlim [ie][QSIZE_D][2][NLEV]       every derived/scratch field [ie][(c)][16][NLEV]
+// One "field tile" = 16*NLEV doubles (9216 B at NLEV=72), contiguous.
+//
+// Thread mapping of every element kernel: one thread per (element, level); the thread keeps the
+// whole 4x4 GLL plane of its level in registers, so the horizontal spectral-element operators
+// (SphereOperators.hpp) are thread-local contractions with the derivative matrix held in
+// constant memory, and consecutive lanes touch consecutive levels (coalesced 8-byte accesses).
+// Vertical scans go through shared memory in the reference's sequential order.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "hommexx_b200.h"
+
+#ifndef HXX_NLEV
+#define HXX_NLEV 72
+#endif
+#ifndef HXX_QSIZE_D
+#define HXX_QSIZE_D 40
+#endif
+
+namespace hxx {
+
+constexpr int NP = 4;
+constexpr int NPSQ = 16;
+constexpr int NLEV = HXX_NLEV;
+constexpr int QSIZE_D = HXX_QSIZE_D;
+constexpr int NTL = 3;   // NUM_TIME_LEVELS
+constexpr int QNTL = 2;  // Q_NUM_TIME_LEVELS
+constexpr int NLF = NPSQ * NLEV;  // doubles per field tile
+
+// PhysicalConstants.hpp:17-22
+constexpr double Rwater_vapor = 461.5;
+constexpr double Rgas = 287.04;
+constexpr double cp = 1005.0;
+constexpr double kappa = Rgas / cp;
+constexpr double rrearth = 1.0 / 6.376e6;
+
+enum { DSS_ETA = 0, DSS_OMEGA = 1, DSS_DIV_VDP_AVE = 2 };  // HommexxEnums.hpp DSSOption
+
+// Per-point geometry record (16 doubles = 128 B), [ie][16][GEO_N]. All threads of an element
+// read the same record: warp-uniform loads served by one L1 transaction.
+enum {
+  G_DINV00 = 0, G_DINV01, G_DINV10, G_DINV11,  // Dinv(a,b) at the point
+  G_D00, G_D01, G_D10, G_D11,                  // D(a,b)
+  G_METDET, G_RMETDET_R,                       // metdet, (1/metdet)*rrearth
+  G_SPHEREMP, G_RSPHEREMP, G_FCOR, G_PHIS, G_MP, G_PAD,
+  GEO_N
+};
+
+// Elements per thread block of the element kernels (threads = EPB*NLEV).
+constexpr int EPB = (NLEV * 4 <= 288) ? 4 : 2;
+
+struct DevConst {
+  double dvv[NP][NP];
+  double hyai[NLEV + 1], hybi[NLEV + 1];
+  double dai[NLEV], dbi[NLEV], dp0[NLEV];
+  double ps0, hyai0;
+};
+
+// ---- boundary-exchange plan (device side) -------------------------------------------------
+// Node-centric DSS: one record per unique GLL boundary node. src[] are the node's member
+// values: >= 0 -> local (elem*16 + pt); < 0 -> halo value index ~src in the receive buffer;
+// NONE -> unused. For each LOCAL member i, ord[i][] lists, in the reference's unpack order
+// (BoundaryExchange.cpp:512-524: edges S,N,W,E for k=0..3, then corners), which other members
+// are added to it.
+constexpr int DSS_NONE = INT32_MIN;
+struct DssNode {
+  int src[4];
+  uint8_t ord[4][3];
+  uint8_t nmem, pad[3];
+};
+static_assert(sizeof(DssNode) == 32, "DssNode layout");
+
+constexpr int MAX_DSS_FIELDS = QSIZE_D + 1;
+struct FieldList {
+  int nf;
+  double* base[MAX_DSS_FIELDS];       // element 0 of each field
+  long long estride[MAX_DSS_FIELDS];  // doubles between consecutive elements
+};
+
+struct Params {  // SimulationParams.hpp
+  int remap_alg, limiter_option, rsplit, qsplit, time_step_type, qsize, state_frequency, ftype;
+  double nu, nu_p, nu_q, nu_s, nu_div, nu_top, hypervis_scaling, nu_ratio1, nu_ratio2;
+  int hypervis_order, hypervis_subcycle;
+  bool moist, disable_diagnostics, consthv, params_set;
+};
+
+struct ConnInfo {  // Connectivity.hpp:21-50
+  int l_lid, l_gid, l_pos, r_lid, r_gid, r_pos;
+  int kind;     // 0 edge, 1 corner, 2 missing
+  int sharing;  // 0 local, 1 shared (remote rank), 2 missing
+  int direction;
+  int remote_pid;
+};
+
+struct Session {
+  bool active = false;
+  int rank = 0, nranks = 1, device = 0;
+  bool comm_set = false;
+  void* nccl = nullptr;  // ncclComm_t
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  Params p{};
+  DevConst hc{};  // host copy of the constants
+  bool have_dvv = false, have_hv = false;
+  int nelemd = 0;
+  int nm1 = 0, n0 = 1, np1 = 2, nstep = 0, nstep0 = 0, n0_qdp = 0, np1_qdp = 1;
+  double rhs_viss = 0.0;
+  bool store_phi = false;
+  std::vector<ConnInfo> conn;  // [nelemd][8]
+
+  // geometry
+  double *geo = nullptr, *metinv = nullptr, *tensorvisc = nullptr, *vec_sph2cart = nullptr;
+  // state
+  double *v = nullptr, *t = nullptr, *dp3d = nullptr, *ps_v = nullptr;
+  double *phi = nullptr, *omega_p = nullptr, *eta_dot_dpdn = nullptr, *derived_vn0 = nullptr,
+         *derived_dp = nullptr, *divdp = nullptr, *divdp_proj = nullptr, *dpdiss_ave = nullptr,
+         *dpdiss_biharmonic = nullptr;
+  double *vtens = nullptr, *ttens = nullptr, *dptens = nullptr;
+  double *vstar = nullptr, *dpdissk = nullptr, *dp_star = nullptr;  // test-visible scratch
+  double *qdp = nullptr, *qtens_biharmonic = nullptr, *qlim = nullptr, *qlim_x = nullptr, *Q = nullptr;
+  // exchange plan
+  DssNode* nodes = nullptr;
+  int nnodes = 0;
+  int* nbr8 = nullptr;  // [nelemd][8] neighbour lid (>=0), ~halo_conn (<0) or DSS_NONE
+  // halo (multi-GPU)
+  int n_halo_pts = 0;           // receive points (edge = 4, corner = 1 per remote connection)
+  int n_send_pts = 0;
+  int* send_src = nullptr;      // [n_send_pts] local elem*16+pt
+  double *sendbuf = nullptr, *recvbuf = nullptr;
+  std::vector<int> peer, peer_send_off, peer_send_cnt, peer_recv_off, peer_recv_cnt;  // in points
+  int n_halo_conn = 0, n_send_conn = 0;  // min/max exchange: one slot per remote connection
+  int* send_conn_elem = nullptr;
+  std::vector<int> peer_csend_off, peer_csend_cnt, peer_crecv_off, peer_crecv_cnt;
+  int* invalid_flag = nullptr;   // device flag: negative/NaN thickness in remap
+  int* h_invalid = nullptr;      // pinned
+  double* diag[8] = {};
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+
+extern Session S;
+
+[[noreturn]] void runtime_abort(const char* msg, int code);
+void cuda_check(cudaError_t e, const char* what, const char* file, int line);
+#define CUDA_OK(x) ::hxx::cuda_check((x), #x, __FILE__, __LINE__)
+#define KERNEL_LAUNCHED() do { ++::hxx::S.launches; CUDA_OK(cudaGetLastError()); } while (0)
+
+// per-translation-unit constant bank (no relocatable device code: each TU owns a copy)
+void register_const_uploader(void (*fn)(const DevConst&));
+void upload_constants();
+#define HXX_DEFINE_CONSTANTS()                                                        \
+  static __constant__ ::hxx::DevConst dc;                                                 \
+  static void hxx_upload_tu(const ::hxx::DevConst& h) {                               \
+    CUDA_OK(cudaMemcpyToSymbolAsync(dc, &h, sizeof(h), 0, cudaMemcpyHostToDevice, ::hxx::S.stream)); \
+  }                                                                                   \
+  static const int hxx_reg_tu = (::hxx::register_const_uploader(&hxx_upload_tu), 0);
+
+// field addressing helpers (host and device)
+__host__ __device__ inline size_t off_v(int ie, int tl, int c) { return (((size_t)ie * NTL + tl) * 2 + c) * NLF; }
+__host__ __device__ inline size_t off_s(int ie, int tl) { return ((size_t)ie * NTL + tl) * NLF; }
+__host__ __device__ inline size_t off_q(int ie, int tq, int q) { return (((size_t)ie * QNTL + tq) * QSIZE_D + q) * NLF; }
+__host__ __device__ inline size_t off_f(int ie) { return (size_t)ie * NLF; }
+
+inline int nblocks_elem(int nelem) { return (nelem + EPB - 1) / EPB; }
+// Threads per block of the sync-free element kernels (flat (element, level) mapping).
+constexpr int TPB = 128;
+inline int nblocks_flat(int nelem) { return (int)(((long long)nelem * NLEV + TPB - 1) / TPB); }
+
+// ---- phases (each defined in its own .cu) -------------------------------------------------
+// dss.cu
+void build_exchange_plan();
+void free_exchange_plan();
+void dss_exchange(const FieldList& fl, bool rspheremp);  // boundary nodes only (interior folded by producer unless told)
+void scale_interior_rspheremp(const FieldList& fl);      // the 4 interior points * rspheremp
+void minmax_exchange();                                  // qlim -> qlim (neighbourhood min/max)
+FieldList fields_caar(int tl);
+FieldList fields_hv();
+FieldList fields_euler(int tq, int dss_opt);
+FieldList fields_qtens();
+double* dss_var(int dss_opt);
+// caar.cu
+void caar_run(int nm1, int n0, int np1, double dt, double eta_ave_w, int n0_qdp, bool with_dss);
+void rk_combine(int nm1, int n0);
+void dp3d_from_ps(int n0);
+void prim_step_init(int n0);
+void update_q(int np1_qdp, int np1);
+// hv.cu
+void hypervis_run(int np1, double dt, double eta_ave_w);
+// euler.cu
+void euler_precompute_divdp();
+void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int dss_opt);
+void euler_qdp_time_avg(int n0_qdp, int np1_qdp);
+// remap.cu
+void vertical_remap(int np1, int np1_qdp);
+void check_remap_flag();
+
+}  // namespace hxx

@@ -1,0 +1,255 @@
+// Element-local spectral-element operators on one level held in registers: s[16], p = igp*4+jgp.
+// Restates SphereOperators.hpp of the reference (file:line per function) with the reference's
+// operation order, so the results are bit-identical to the CPU oracle when compiled with
+// --fmad=false. The including translation unit must have HXX_DEFINE_CONSTANTS() above.
+#pragma once
+#include "hxx.cuh"
+
+namespace hxx {
+
+#define HXX_UNROLL _Pragma("unroll")
+
+__device__ __forceinline__ double geo_ld(const double* __restrict__ g, int p, int c) {
+  return __ldg(g + p * GEO_N + c);
+}
+
+// load / store one level of a field tile ([16][NLEV], the thread's level already added to ptr)
+__device__ __forceinline__ void plane_load(const double* __restrict__ f, double (&s)[NPSQ]) {
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) s[p] = f[p * NLEV];
+}
+__device__ __forceinline__ void plane_store(double* __restrict__ f, const double (&s)[NPSQ]) {
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) f[p * NLEV] = s[p];
+}
+
+// dx[p] = sum_m Dvv(j,m) s(i,m) ; dy[p] = sum_m Dvv(i,m) s(m,j)   (m ascending)
+__device__ __forceinline__ void deriv_pair(const double (&sx)[NPSQ], const double (&sy)[NPSQ], double (&dx)[NPSQ],
+                                           double (&dy)[NPSQ]) {
+  HXX_UNROLL
+  for (int i = 0; i < NP; ++i) {
+    HXX_UNROLL
+    for (int j = 0; j < NP; ++j) {
+      double a = dc.dvv[j][0] * sx[i * NP + 0];
+      double b = dc.dvv[i][0] * sy[0 * NP + j];
+      HXX_UNROLL
+      for (int m = 1; m < NP; ++m) {
+        a += dc.dvv[j][m] * sx[i * NP + m];
+        b += dc.dvv[i][m] * sy[m * NP + j];
+      }
+      dx[i * NP + j] = a;
+      dy[i * NP + j] = b;
+    }
+  }
+}
+
+// SphereOperators.hpp:293-319
+__device__ __forceinline__ void gradient_sphere(const double* __restrict__ g, const double (&s)[NPSQ],
+                                                double (&g0)[NPSQ], double (&g1)[NPSQ]) {
+  double dx[NPSQ], dy[NPSQ];
+  deriv_pair(s, s, dx, dy);
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) {
+    const double v0 = dx[p] * rrearth, v1 = dy[p] * rrearth;
+    g0[p] = geo_ld(g, p, G_DINV00) * v0 + geo_ld(g, p, G_DINV01) * v1;
+    g1[p] = geo_ld(g, p, G_DINV10) * v0 + geo_ld(g, p, G_DINV11) * v1;
+  }
+}
+
+// :323-348
+__device__ __forceinline__ void gradient_sphere_update(const double* __restrict__ g, const double (&s)[NPSQ],
+                                                       double (&g0)[NPSQ], double (&g1)[NPSQ]) {
+  double dx[NPSQ], dy[NPSQ];
+  deriv_pair(s, s, dx, dy);
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) {
+    const double v0 = dx[p] * rrearth, v1 = dy[p] * rrearth;
+    g0[p] += geo_ld(g, p, G_DINV00) * v0 + geo_ld(g, p, G_DINV01) * v1;
+    g1[p] += geo_ld(g, p, G_DINV10) * v0 + geo_ld(g, p, G_DINV11) * v1;
+  }
+}
+
+// :352-392
+__device__ __forceinline__ void divergence_sphere(const double* __restrict__ g, const double (&v0)[NPSQ],
+                                                  const double (&v1)[NPSQ], double (&div)[NPSQ]) {
+  double gv0[NPSQ], gv1[NPSQ];
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) {
+    const double md = geo_ld(g, p, G_METDET);
+    gv0[p] = (geo_ld(g, p, G_DINV00) * v0[p] + geo_ld(g, p, G_DINV10) * v1[p]) * md;
+    gv1[p] = (geo_ld(g, p, G_DINV01) * v0[p] + geo_ld(g, p, G_DINV11) * v1[p]) * md;
+  }
+  double dx[NPSQ], dy[NPSQ];
+  deriv_pair(gv0, gv1, dx, dy);
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) div[p] = (dx[p] + dy[p]) * geo_ld(g, p, G_RMETDET_R);
+}
+
+// :494-533
+__device__ __forceinline__ void vorticity_sphere(const double* __restrict__ g, const double (&u)[NPSQ],
+                                                 const double (&v)[NPSQ], double (&vort)[NPSQ]) {
+  double c0[NPSQ], c1[NPSQ];
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) {
+    c0[p] = geo_ld(g, p, G_D00) * u[p] + geo_ld(g, p, G_D01) * v[p];
+    c1[p] = geo_ld(g, p, G_D10) * u[p] + geo_ld(g, p, G_D11) * v[p];
+  }
+  double dvdx[NPSQ], dudy[NPSQ];
+  deriv_pair(c1, c0, dvdx, dudy);
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) vort[p] = (dvdx[p] - dudy[p]) * geo_ld(g, p, G_RMETDET_R);
+}
+
+// :538-583 (inputs are the sphere-basis vector; transformed internally)
+__device__ __forceinline__ void divergence_sphere_wk(const double* __restrict__ g, const double (&v0)[NPSQ],
+                                                     const double (&v1)[NPSQ], double (&div)[NPSQ]) {
+  double s0[NPSQ], s1[NPSQ];  // spheremp * (Dinv^T v)
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) {
+    const double w0 = geo_ld(g, p, G_DINV00) * v0[p] + geo_ld(g, p, G_DINV10) * v1[p];
+    const double w1 = geo_ld(g, p, G_DINV01) * v0[p] + geo_ld(g, p, G_DINV11) * v1[p];
+    const double sm = geo_ld(g, p, G_SPHEREMP);
+    s0[p] = sm * w0;
+    s1[p] = sm * w1;
+  }
+  HXX_UNROLL
+  for (int n = 0; n < NP; ++n) {
+    HXX_UNROLL
+    for (int m = 0; m < NP; ++m) {
+      double dd = -((s0[n * NP + 0] * dc.dvv[0][m] + s1[0 * NP + m] * dc.dvv[0][n]) * rrearth);
+      HXX_UNROLL
+      for (int j = 1; j < NP; ++j)
+        dd -= (s0[n * NP + j] * dc.dvv[j][m] + s1[j * NP + m] * dc.dvv[j][n]) * rrearth;
+      div[n * NP + m] = dd;
+    }
+  }
+}
+
+// :588-597
+__device__ __forceinline__ void laplace_simple(const double* __restrict__ g, const double (&s)[NPSQ],
+                                               double (&lap)[NPSQ]) {
+  double g0[NPSQ], g1[NPSQ];
+  gradient_sphere(g, s, g0, g1);
+  divergence_sphere_wk(g, g0, g1, lap);
+}
+
+// :604-635 — tv = this element's tensorVisc [2][2][16]
+__device__ __forceinline__ void laplace_tensor(const double* __restrict__ g, const double* __restrict__ tv,
+                                               const double (&s)[NPSQ], double (&lap)[NPSQ]) {
+  double g0[NPSQ], g1[NPSQ], t0[NPSQ], t1[NPSQ];
+  gradient_sphere(g, s, g0, g1);
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) {
+    t0[p] = __ldg(tv + 0 * NPSQ + p) * g0[p] + __ldg(tv + 2 * NPSQ + p) * g1[p];
+    t1[p] = __ldg(tv + 1 * NPSQ + p) * g0[p] + __ldg(tv + 3 * NPSQ + p) * g1[p];
+  }
+  divergence_sphere_wk(g, t0, t1, lap);
+}
+
+// :714-748 — mi = this element's metinv [2][2][16]
+__device__ __forceinline__ void grad_sphere_wk_testcov(const double* __restrict__ g, const double* __restrict__ mi,
+                                                       const double (&s)[NPSQ], double (&g0)[NPSQ],
+                                                       double (&g1)[NPSQ]) {
+  HXX_UNROLL
+  for (int n = 0; n < NP; ++n) {
+    HXX_UNROLL
+    for (int m = 0; m < NP; ++m) {
+      const int p = n * NP + m;
+      const double md = geo_ld(g, p, G_METDET);
+      const double mi00 = __ldg(mi + 0 * NPSQ + p), mi01 = __ldg(mi + 1 * NPSQ + p), mi10 = __ldg(mi + 2 * NPSQ + p),
+                   mi11 = __ldg(mi + 3 * NPSQ + p);
+      double b0 = 0.0, b1 = 0.0;
+      HXX_UNROLL
+      for (int j = 0; j < NP; ++j) {
+        const double mpnj = geo_ld(g, n * NP + j, G_MP), mpjm = geo_ld(g, j * NP + m, G_MP);
+        const double snj = s[n * NP + j], sjm = s[j * NP + m];
+        const double djm = dc.dvv[j][m], djn = dc.dvv[j][n];
+        const double x0 = mpnj * mi00 * md * snj * djm + mpjm * mi01 * md * sjm * djn;
+        const double x1 = mpnj * mi10 * md * snj * djm + mpjm * mi11 * md * sjm * djn;
+        if (j == 0) { b0 = -x0; b1 = -x1; }
+        else { b0 -= x0; b1 -= x1; }
+      }
+      g0[p] = (geo_ld(g, p, G_D00) * b0 + geo_ld(g, p, G_D10) * b1) * rrearth;
+      g1[p] = (geo_ld(g, p, G_D01) * b0 + geo_ld(g, p, G_D11) * b1) * rrearth;
+    }
+  }
+}
+
+// :683-710
+__device__ __forceinline__ void curl_sphere_wk_testcov_update(const double* __restrict__ g, double alpha, double beta,
+                                                              const double (&s)[NPSQ], double (&c0)[NPSQ],
+                                                              double (&c1)[NPSQ]) {
+  double ms[NPSQ];
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) ms[p] = geo_ld(g, p, G_MP) * s[p];
+  HXX_UNROLL
+  for (int n = 0; n < NP; ++n) {
+    HXX_UNROLL
+    for (int m = 0; m < NP; ++m) {
+      const int p = n * NP + m;
+      double sb0 = -(ms[0 * NP + m] * dc.dvv[0][n]);
+      double sb1 = ms[n * NP + 0] * dc.dvv[0][m];
+      HXX_UNROLL
+      for (int j = 1; j < NP; ++j) {
+        sb0 -= ms[j * NP + m] * dc.dvv[j][n];
+        sb1 += ms[n * NP + j] * dc.dvv[j][m];
+      }
+      c0[p] = beta * c0[p] + alpha * (geo_ld(g, p, G_D00) * sb0 + geo_ld(g, p, G_D10) * sb1) * rrearth;
+      c1[p] = beta * c1[p] + alpha * (geo_ld(g, p, G_D01) * sb0 + geo_ld(g, p, G_D11) * sb1) * rrearth;
+    }
+  }
+}
+
+// :818-862
+__device__ __forceinline__ void vlaplace_sphere_wk_contra(const double* __restrict__ g, const double* __restrict__ mi,
+                                                          double nu_ratio, const double (&v0)[NPSQ],
+                                                          const double (&v1)[NPSQ], double (&l0)[NPSQ],
+                                                          double (&l1)[NPSQ]) {
+  double sc[NPSQ], gc0[NPSQ], gc1[NPSQ];
+  divergence_sphere(g, v0, v1, sc);
+  if (nu_ratio > 0 && nu_ratio != 1.0) {
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) sc[p] *= nu_ratio;
+  }
+  grad_sphere_wk_testcov(g, mi, sc, gc0, gc1);
+  vorticity_sphere(g, v0, v1, sc);
+  curl_sphere_wk_testcov_update(g, -1.0, 1.0, sc, gc0, gc1);
+  const double re2 = rrearth * rrearth;
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) {
+    const double f = 2.0 * geo_ld(g, p, G_SPHEREMP);
+    l0[p] = f * v0[p] * re2 + gc0[p];
+    l1[p] = f * v1[p] * re2 + gc1[p];
+  }
+}
+
+// :752-814 — vs = this element's vec_sph2cart [2][3][16]
+__device__ __forceinline__ void vlaplace_sphere_wk_cartesian(const double* __restrict__ g, const double* __restrict__ tv,
+                                                             const double* __restrict__ vs, const double (&v0)[NPSQ],
+                                                             const double (&v1)[NPSQ], double (&l0)[NPSQ],
+                                                             double (&l1)[NPSQ]) {
+  double acc0[NPSQ], acc1[NPSQ];
+  for (int c = 0; c < 3; ++c) {
+    double comp[NPSQ], lap[NPSQ];
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p)
+      comp[p] = __ldg(vs + (0 * 3 + c) * NPSQ + p) * v0[p] + __ldg(vs + (1 * 3 + c) * NPSQ + p) * v1[p];
+    laplace_tensor(g, tv, comp, lap);
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) {
+      const double a = __ldg(vs + (0 * 3 + c) * NPSQ + p) * lap[p], b = __ldg(vs + (1 * 3 + c) * NPSQ + p) * lap[p];
+      if (c == 0) { acc0[p] = a; acc1[p] = b; }
+      else { acc0[p] += a; acc1[p] += b; }
+    }
+  }
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) {
+    const double sm = geo_ld(g, p, G_SPHEREMP);
+    l0[p] = acc0[p] + 2.0 * sm * v0[p] * rrearth * rrearth;
+    l1[p] = acc1[p] + 2.0 * sm * v1[p] * rrearth * rrearth;
+  }
+}
+
+__device__ __forceinline__ bool is_interior_pt(int p) { return p == 5 || p == 6 || p == 9 || p == 10; }
+
+}  // namespace hxx

@@ -107,6 +107,9 @@ const char* hommexx_b200_backend(void);
  * nccl_unique_id = the 128-byte ncclUniqueId created on rank 0 and broadcast by the host
  * (torch.distributed / MPI_Bcast). Must be called before init_connectivity when size > 1. */
 void hommexx_b200_set_comm(int rank, int size, int device, const void* nccl_unique_id);
+/* Fills out128 with a fresh ncclUniqueId (call on rank 0, broadcast, pass to set_comm).
+ * Returns 0 on success, nonzero if NCCL is unavailable in this build. */
+int hommexx_b200_nccl_unique_id(void* out128);
 /* Number of kernels this library has launched since session start (bench's gpu_launches). */
 int64_t hommexx_b200_launch_count(void);
 /* Blocks until all device work issued so far has completed. */
