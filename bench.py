@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the preqx dycore timestep (BASELINE.json: element-steps/s and SYPD at ne30,
+nlev 72, qsize 40 on B200, with the fraction of the HBM roofline).
+
+A "step" of this bench is ONE prim_run_subcycle_c call = rsplit*qsplit dynamics steps (3 for the
+ne30 benchmark namelist test/reg_test/benchmarks/v1/homme-ne30-v1.nl) on synthetic
+Jablonowski-Williamson baroclinic-wave initial data. `value` counts DYNAMICS steps:
+element-steps/s = elements * dynamics steps / second, whole job.
+
+  python bench.py [--gpus N --steps K --warmup W]         the CUDA dycore (one process per GPU;
+                                                          for N > 1 launch with torch.distributed.run)
+  python bench.py --impl reference ...                    the CPU arm: the reference's algorithm on
+                                                          the host cores (oracle port; the reference's
+                                                          own Kokkos/Fortran build needs toolchains
+                                                          this image lacks)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+F_BYTES = 16 * 72 * 8  # one field tile of one element at nlev = 72
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(args, n_gpus):
+    """N=1: BASELINE configs[1] (ne30). N>1: weak scaling, ~5400 elements per GPU
+    (ne = round(sqrt(900 N)): 42, 60, 85 for N = 2, 4, 8), same namelist."""
+    from hommexx_b200 import homme
+    if args.ne:
+        ne = args.ne
+    elif n_gpus == 1:
+        ne = 30
+    else:
+        ne = int(round((900.0 * n_gpus) ** 0.5))
+    over = dict(ne=ne, npart=n_gpus)
+    if args.qsize:
+        over.update(qsize=args.qsize)
+    return homme.preset("ne30", **over)
+
+
+def euler_advect_bytes(nelem, qsize):
+    """Algorithmic HBM bytes of one euler_advect launch, averaged over the 3 stages of a tracer
+    step: per tracer read qdp + write qdp (+ read qtens_biharmonic on the
+    hyperviscosity stage) + 2 qlim rows; per element read derived_dp, divdp_proj, divdp, vn0 (2)
+    (+ dpdiss_biharmonic on stage 3) and read+write the DSS variable."""
+    per_stage = []
+    for hv in (0, 0, 1):
+        per_elem = (2 + hv) * qsize * F_BYTES + qsize * 2 * 72 * 8 + (5 + hv + 2) * F_BYTES
+        per_stage.append(per_elem)
+    return nelem * sum(per_stage) / 3.0
+
+
+def step_bytes_per_elem_step(cfg):
+    """algorithmic tiles per element per dynamics step."""
+    q, hv, rs, qs = cfg.qsize, cfg.hypervis_subcycle, cfg.rsplit, cfg.qsplit
+    caar = 14 + 3 * 12 + 18 + 5 * 11 + 12
+    hvt = hv * 54
+    euler = (45 + 31 * q) / qs
+    remap = (2 * (q + 3) + 6) / (rs * qs)
+    updq = 2 * q / (rs * qs)
+    misc = 10
+    return (caar + hvt + euler + remap + updq + misc) * F_BYTES
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's algorithm, all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from hommexx_b200 import homme
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    ne_s = args.ref_ne
+    cfg = workload(args, 1)
+    scfg = homme.preset("ne30", ne=ne_s, qsize=cfg.qsize)
+    h = homme.Homme(scfg, homme.ORACLE_LIB)
+    h.init_dycore()
+    dyn = scfg.rsplit * scfg.qsplit
+    for _ in range(args.warmup):
+        h.run_subcycle()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h.run_subcycle()
+    dt = time.perf_counter() - t0
+    val = h.nelem * dyn * args.steps / dt
+    sample = (f"oracle port (CPU restatement of the reference functors, gcc -O3 -fopenmp), ne={ne_s} "
+              f"({h.nelem} elements) nlev {scfg.nlev} qsize {scfg.qsize}, same namelist as the GPU arm; "
+              f"element-steps/s is per-element throughput, so the sample is size-independent")
+    h.close()
+    out = {"impl": "reference", "metric": "element_steps_per_s", "value": val, "unit": "element-steps/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "sypd": None,
+           "config": {"workload": f"preqx ne{cfg.ne} nlev{cfg.nlev} qsize{cfg.qsize} (timed on a bounded sample)",
+                      "sample": sample},
+           "cpu_baseline": {"value": val, "unit": "element-steps/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "element-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def pin_driver_arrays(h, torch):
+    """Page-lock the driver's Fortran-layout arrays so the e2e copies run from pinned memory."""
+    rt = torch.cuda.cudart()
+    pinned = []
+    for name in ("v", "T", "dp3d", "Qdp", "Q", "ps_v", "omega_p"):
+        a = h.array(name)
+        r = rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+        if int(r) == 0:
+            pinned.append(a.ctypes.data)
+    return pinned
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--ne", type=int, default=0, help="override the mesh (default: 30 at N=1, weak-scaled for N>1)")
+    ap.add_argument("--qsize", type=int, default=0)
+    ap.add_argument("--ref-ne", type=int, default=10, help="mesh of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    from hommexx_b200 import homme
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+    n_gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the dycore has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg = workload(args, n_gpus)
+    cfg.part_id = rank
+    libpath = homme.cuda_lib_path(cfg.nlev, cfg.qsize_d)
+    lib = homme.load_dycore(libpath)
+    lib.hommexx_b200_event_elapsed_ms.restype = C.c_double
+    lib.hommexx_b200_profile.argtypes = [C.c_ulonglong]
+    lib.hommexx_b200_profile_read.restype = C.c_double
+    lib.hommexx_b200_profile_read.argtypes = [C.c_int, C.POINTER(C.c_int64)]
+    lib.hommexx_b200_kernel_id.argtypes = [C.c_char_p]
+    lib.hommexx_b200_kernel_name.restype = C.c_char_p
+    if world > 1:
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            raw = (C.c_ubyte * 128)()
+            assert lib.hommexx_b200_nccl_unique_id(raw) == 0
+            idbuf.copy_(torch.tensor(list(raw), dtype=torch.uint8))
+        dist.broadcast(idbuf, 0)
+        raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
+        lib.hommexx_b200_set_comm(rank, world, local_rank, raw)
+    else:
+        lib.hommexx_b200_set_comm(0, 1, local_rank, None)
+
+    t_setup = time.perf_counter()
+    h = homme.Homme(cfg, libpath)
+    h.init_dycore()
+    log(f"[rank {rank}] setup {time.perf_counter() - t_setup:.1f}s: ne={cfg.ne} nelem={h.nelem} local={h.nelemd} "
+        f"qsize={cfg.qsize} nlev={cfg.nlev}")
+    dyn = cfg.rsplit * cfg.qsplit
+
+    def barrier():
+        lib.hommexx_b200_sync()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kid = lib.hommexx_b200_kernel_id(b"euler_advect")
+    for _ in range(args.warmup):
+        h.run_subcycle()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.hommexx_b200_profile(1 << kid)           # CUDA-event pair around every launch of the dominant kernel
+    l0 = lib.hommexx_b200_launch_count()
+    barrier()
+    lib.hommexx_b200_event_record(0)
+    for _ in range(args.steps):
+        h.run_subcycle()
+    lib.hommexx_b200_event_record(1)
+    barrier()
+    ms = lib.hommexx_b200_event_elapsed_ms(0, 1)
+    launches = lib.hommexx_b200_launch_count() - l0
+    clocks = sampler.stop()
+    nl = C.c_int64()
+    k_ms = lib.hommexx_b200_profile_read(kid, C.byref(nl))
+    lib.hommexx_b200_profile(0)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = h.nelem * dyn * args.steps / (ms * 1e-3)
+    sypd = (dyn * args.steps / (ms * 1e-3)) * cfg.tstep / 365.0  # simulated years per wall day
+
+    peak, peak_src = peaks()
+    adv_bytes = euler_advect_bytes(h.nelemd, cfg.qsize)
+    k_avg_ms = k_ms / max(1, nl.value)
+    achieved = adv_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
+    traffic = None
+    tf = ROOT / "profiles" / "roofline_traffic.json"
+    if tf.exists():
+        traffic = json.loads(tf.read_text()).get("euler_advect_dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "euler_advect_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": adv_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": nl.value,
+                "kernel_share_of_step": k_ms / ms if ms > 0 else None}
+    step_bytes = step_bytes_per_elem_step(cfg)
+    step_gbs = value / n_gpus * step_bytes / 1e9
+
+    # ---- per-kernel breakdown (untimed extra pass; CUDA events around every launch) ----------
+    breakdown = None
+    if not args.no_breakdown:
+        lib.hommexx_b200_profile((1 << 19) - 1)
+        lib.hommexx_b200_event_record(2)
+        h.run_subcycle()
+        lib.hommexx_b200_event_record(3)
+        tot = lib.hommexx_b200_event_elapsed_ms(2, 3)
+        breakdown = {}
+        for i in range(19):
+            n = C.c_int64()
+            t = lib.hommexx_b200_profile_read(i, C.byref(n))
+            if n.value:
+                breakdown[lib.hommexx_b200_kernel_name(i).decode()] = {"launches": n.value, "ms": round(t, 4),
+                                                                       "share": round(t / tot, 4)}
+        breakdown["_subcycle_ms"] = round(tot, 4)
+        lib.hommexx_b200_profile(0)
+        if rank == 0:
+            log("per-kernel breakdown of one prim_run_subcycle_c:")
+            for k_, v_ in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"] if isinstance(kv[1], dict) else 0):
+                log(f"  {k_:34s} {v_}")
+
+    # ---- e2e: the reference-facing C ABI with HOST buffers, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        pin_driver_arrays(h, torch)
+        st = h.state()
+        h2d = sum(st[k].nbytes for k in ("v", "T", "dp3d", "Qdp", "ps_v"))
+        d2h = sum(st[k].nbytes for k in ("v", "T", "dp3d", "Qdp", "Q", "ps_v", "omega_p"))
+        h.push_results()            # warm the staging buffers
+        barrier()
+        t0 = time.perf_counter()
+        h.upload_state()            # init_elements_states_c: host (Fortran layout) -> device, transposed
+        for _ in range(args.steps):
+            h.run_subcycle()        # prim_run_subcycle_c (host scalars in/out, device flag read back)
+        h.push_results()            # cxx_push_results_to_f90: device -> host, all time levels
+        barrier()
+        e_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_s = float(t.item())
+        e2e = {"value": h.nelem * dyn * args.steps / e_s, "unit": "element-steps/s",
+               "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+               "what": "init_elements_states_c + steps x prim_run_subcycle_c + cxx_push_results_to_f90 from pinned "
+                       "host arrays in the Fortran layout (the reference benchmark pushes once per run: statefreq=9999)"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1) -------------------------------------------------
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        scfg = homme.preset("ne30", ne=args.ref_ne, qsize=cfg.qsize)
+        ho = homme.Homme(scfg, homme.ORACLE_LIB)
+        ho.init_dycore()
+        ho.run_subcycle()
+        t0 = time.perf_counter()
+        nrep = 3
+        for _ in range(nrep):
+            ho.run_subcycle()
+        dt = time.perf_counter() - t0
+        cpu = {"value": ho.nelem * dyn * nrep / dt, "unit": "element-steps/s", "cores": cores, "kind": "port",
+               "sample": f"oracle port, {nrep} subcycle calls at ne={args.ref_ne} ({ho.nelem} elements), nlev {scfg.nlev}, "
+                         f"qsize {scfg.qsize}, OpenMP over elements on all host cores"}
+        ho.close()
+
+    if rank == 0:
+        out = {"metric": "element_steps_per_s", "value": value, "unit": "element-steps/s", "n_gpus": n_gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "sypd": sypd, "dynamics_steps_per_bench_step": dyn,
+               "config": {"workload": f"preqx ne{cfg.ne} ({h.nelem} elements) nlev{cfg.nlev} qsize{cfg.qsize}, JW baroclinic "
+                                      f"wave, homme-ne30-v1.nl namelist (tstep {cfg.tstep:g} rsplit {cfg.rsplit} qsplit "
+                                      f"{cfg.qsplit} hypervis_subcycle {cfg.hypervis_subcycle} limiter {cfg.limiter_option})",
+                          "partition": f"SFC, {n_gpus} part(s), {h.nelemd} elements on rank 0",
+                          "l2": "working set (>9 GB at ne30) far exceeds the 126 MB L2; no flush needed",
+                          "step": "one prim_run_subcycle_c call"},
+               "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
+               "step_roofline": {"algorithmic_bytes_per_element_step": step_bytes, "achieved_gbs_per_gpu": step_gbs,
+                                 "frac": step_gbs / peak, "peak": peak},
+               "e2e": e2e, "cpu_baseline": cpu, "breakdown": breakdown}
+        print(json.dumps(out), flush=True)
+    h.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -218,8 +218,9 @@ void caar_run(int nm1, int n0, int np1, double dt, double eta_ave_w, int n0_qdp,
     CUDA_OK(cudaFuncSetAttribute(caar_kernel<EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
+  PROBE(K_CAAR);
   caar_kernel<EPB><<<nblocks_elem(S.nelemd), EPB * NLEV, smem, S.stream>>>(a);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_CAAR);
   if (with_dss) dss_exchange(fields_caar(np1), true);  // CaarFunctor.cpp:113
 }
 
@@ -242,8 +243,9 @@ __global__ void rk_combine_kernel(double* __restrict__ v, double* __restrict__ t
 }
 void rk_combine(int nm1, int n0) {
   if (!S.nelemd) return;
+  PROBE(K_RK_COMBINE);
   rk_combine_kernel<<<S.nelemd, 288, 0, S.stream>>>(S.v, S.t, S.dp3d, nm1, n0);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_RK_COMBINE);
 }
 
 // prim_driver.cpp:98-111
@@ -258,8 +260,9 @@ __global__ void dp3d_from_ps_kernel(double* __restrict__ dp3d, const double* __r
 }
 void dp3d_from_ps(int n0) {
   if (!S.nelemd) return;
+  PROBE(K_DP3D_FROM_PS);
   dp3d_from_ps_kernel<<<S.nelemd, 288, 0, S.stream>>>(S.dp3d, S.ps_v, n0);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_DP3D_FROM_PS);
 }
 
 // prim_step.cpp:51-66
@@ -279,8 +282,9 @@ void prim_step_init(int n0) {
     CUDA_OK(cudaMemsetAsync(S.dpdiss_ave, 0, f3, S.stream));
     CUDA_OK(cudaMemsetAsync(S.dpdiss_biharmonic, 0, f3, S.stream));
   }
+  PROBE(K_STEP_INIT);
   derived_dp_kernel<<<S.nelemd, 288, 0, S.stream>>>(S.derived_dp, S.dp3d, n0);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_STEP_INIT);
 }
 
 // prim_driver.cpp:171-206
@@ -298,8 +302,9 @@ __global__ void update_q_kernel(double* __restrict__ Q, const double* __restrict
 }
 void update_q(int np1_qdp, int np1) {
   if (!S.nelemd || !S.p.qsize) return;
+  PROBE(K_UPDATE_Q);
   update_q_kernel<<<dim3(S.nelemd, S.p.qsize), 288, 0, S.stream>>>(S.Q, S.qdp, S.ps_v, np1_qdp, np1);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_UPDATE_Q);
 }
 
 }  // namespace hxx

@@ -337,33 +337,38 @@ static void halo_sendrecv(const std::vector<int>& soff, const std::vector<int>& 
 
 void dss_exchange(const FieldList& fl, bool rspheremp) {
   if (S.n_send_pts) {
+    PROBE(K_HALO_PACK);
     halo_pack_kernel<<<dim3(S.n_send_pts, fl.nf), 96, 0, S.stream>>>(S.send_src, S.n_send_pts, fl, S.sendbuf);
-    KERNEL_LAUNCHED();
+    KERNEL_LAUNCHED(K_HALO_PACK);
     halo_sendrecv(S.peer_send_off, S.peer_send_cnt, S.peer_recv_off, S.peer_recv_cnt, (size_t)fl.nf * NLEV);
   }
   if (!S.nnodes) return;
   const dim3 grid((S.nnodes + NODES_PB - 1) / NODES_PB, (fl.nf + DSS_FPB - 1) / DSS_FPB);
+  PROBE(K_DSS);
   if (rspheremp) dss_nodes_kernel<true><<<grid, NODES_PB * NLEV, 0, S.stream>>>(S.nodes, S.nnodes, fl, S.geo, S.recvbuf);
   else dss_nodes_kernel<false><<<grid, NODES_PB * NLEV, 0, S.stream>>>(S.nodes, S.nnodes, fl, S.geo, S.recvbuf);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_DSS);
 }
 
 void scale_interior_rspheremp(const FieldList& fl) {
   if (!S.nelemd) return;
+  PROBE(K_DSS);
   scale_interior_kernel<<<dim3(S.nelemd, fl.nf), 96, 0, S.stream>>>(fl, S.geo, S.nelemd);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_DSS);
 }
 
 void minmax_exchange() {
   const int nq = S.p.qsize;
   if (!S.nelemd || !nq) return;
   if (S.n_send_conn) {
+    PROBE(K_HALO_PACK);
     minmax_pack_kernel<<<dim3(S.n_send_conn, nq), 96, 0, S.stream>>>(S.send_conn_elem, S.qlim, nq, S.sendbuf);
-    KERNEL_LAUNCHED();
+    KERNEL_LAUNCHED(K_HALO_PACK);
     halo_sendrecv(S.peer_csend_off, S.peer_csend_cnt, S.peer_crecv_off, S.peer_crecv_cnt, (size_t)nq * 2 * NLEV);
   }
+  PROBE(K_MINMAX);
   minmax_kernel<<<dim3(S.nelemd, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, S.recvbuf, nq);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_MINMAX);
   std::swap(S.qlim, S.qlim_x);
 }
 

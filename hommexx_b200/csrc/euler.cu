@@ -218,9 +218,10 @@ __global__ void euler_time_avg_kernel(double* __restrict__ qdp, int n0_qdp, int 
 
 void euler_precompute_divdp() {
   if (!S.nelemd) return;
+  PROBE(K_EULER_DIVDP);
   euler_divdp_kernel<<<nblocks_flat(S.nelemd), TPB, 0, S.stream>>>(S.geo, S.derived_vn0, S.divdp, S.divdp_proj,
                                                                          S.nelemd);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_EULER_DIVDP);
 }
 
 static int tracer_chunk() {
@@ -242,8 +243,9 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
               n0_qdp, np1_qdp, dt, rhs_multiplier * dt, S.p.nu_p, S.p.nu_q, S.rhs_viss, mode, S.p.limiter_option,
               S.p.consthv ? 1 : 0};
   const dim3 grid(nblocks_flat(S.nelemd), (nq + a.qchunk - 1) / a.qchunk);
+  PROBE(K_EULER_QMINMAX);
   euler_qminmax_kernel<<<grid, TPB, 0, S.stream>>>(a);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_EULER_QMINMAX);
   if (mode == 0) {
     minmax_exchange();  // neighbor_minmax :504-507
   } else if (mode == 2) {
@@ -264,19 +266,22 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   double* fdss = a.f_dss;
   const bool separate = (fdss == S.divdp_proj && a.rhsmdt != 0.0);
   if (separate) a.f_dss = nullptr;
+  PROBE(K_EULER_ADVECT);
   euler_advect_kernel<<<grid, TPB, smem, S.stream>>>(a);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_EULER_ADVECT);
   if (separate) {
+    PROBE(K_EULER_FDSS);
     euler_fdss_kernel<<<S.nelemd, 288, 0, S.stream>>>(fdss, S.geo);
-    KERNEL_LAUNCHED();
+    KERNEL_LAUNCHED(K_EULER_FDSS);
   }
   dss_exchange(fields_euler(np1_qdp, dss_opt), true);  // exchange_qdp_dss_var :509-512
 }
 
 void euler_qdp_time_avg(int n0_qdp, int np1_qdp) {
   if (!S.nelemd || !S.p.qsize) return;
+  PROBE(K_EULER_TAVG);
   euler_time_avg_kernel<<<dim3(S.nelemd, S.p.qsize), 288, 0, S.stream>>>(S.qdp, n0_qdp, np1_qdp);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_EULER_TAVG);
 }
 
 }  // namespace hxx

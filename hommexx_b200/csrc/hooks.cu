@@ -73,9 +73,10 @@ extern "C" void hxx_sphere_op(const char* op, int ie, const double* in, double* 
   CUDA_OK(cudaMalloc(&d_in, 2 * NLF * 8));
   CUDA_OK(cudaMalloc(&d_out, 2 * NLF * 8));
   CUDA_OK(cudaMemcpyAsync(d_in, in, (size_t)n_in * NLF * 8, cudaMemcpyHostToDevice, S.stream));
+  PROBE(K_HOOK);
   sphere_op_kernel<<<1, ((NLEV + 31) / 32) * 32, 0, S.stream>>>(code, S.geo + (size_t)ie * NPSQ * GEO_N,
                                                                S.metinv + (size_t)ie * 4 * NPSQ, d_in, d_out, nu_ratio);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_HOOK);
   CUDA_OK(cudaMemcpyAsync(out, d_out, (size_t)n_out * NLF * 8, cudaMemcpyDeviceToHost, S.stream));
   CUDA_OK(cudaStreamSynchronize(S.stream));
   cudaFree(d_in);
@@ -93,8 +94,9 @@ extern "C" void hxx_limiter(int limiter_option, int nsets, const double* sphweig
   CUDA_OK(cudaMemcpyAsync(d_pt, ptens, nf, cudaMemcpyHostToDevice, S.stream));
   CUDA_OK(cudaMemcpyAsync(d_ql, qlim, nq, cudaMemcpyHostToDevice, S.stream));
   const int nt = nsets * NLEV;
+  PROBE(K_HOOK);
   limiter_kernel<<<(nt + 127) / 128, 128, 0, S.stream>>>(limiter_option, nsets, d_w, d_dp, d_pt, d_ql);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_HOOK);
   CUDA_OK(cudaMemcpyAsync(ptens, d_pt, nf, cudaMemcpyDeviceToHost, S.stream));
   CUDA_OK(cudaMemcpyAsync(qlim, d_ql, nq, cudaMemcpyDeviceToHost, S.stream));
   CUDA_OK(cudaStreamSynchronize(S.stream));

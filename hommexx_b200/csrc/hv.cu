@@ -172,14 +172,17 @@ void hypervis_run(int np1, double dt_in, double eta_ave_w) {
            p.nu_p, p.nu_top, p.nu_ratio1, p.nu_ratio2, p.hypervis_subcycle, p.consthv ? 1 : 0};
   const int nb = nblocks_flat(S.nelemd);
   for (int icycle = 0; icycle < p.hypervis_subcycle; ++icycle) {
+    PROBE(K_HV_FIRST);
     hv_first_laplace_kernel<<<nb, TPB, 0, S.stream>>>(a);
-    KERNEL_LAUNCHED();
+    KERNEL_LAUNCHED(K_HV_FIRST);
     dss_exchange(fields_hv(), true);
+    PROBE(K_HV_SECOND);
     hv_second_laplace_pre_exchange_kernel<<<nb, TPB, 0, S.stream>>>(a);
-    KERNEL_LAUNCHED();
+    KERNEL_LAUNCHED(K_HV_SECOND);
     dss_exchange(fields_hv(), false);
+    PROBE(K_HV_UPDATE);
     hv_update_states_kernel<<<S.nelemd, 288, 0, S.stream>>>(a);
-    KERNEL_LAUNCHED();
+    KERNEL_LAUNCHED(K_HV_UPDATE);
   }
 }
 

@@ -61,6 +61,14 @@ enum {
 // Elements per thread block of the element kernels (threads = EPB*NLEV).
 constexpr int EPB = (NLEV * 4 <= 288) ? 4 : 2;
 
+// kernel classes for launch accounting and the per-kernel CUDA-event probes
+enum KernelId {
+  K_CAAR = 0, K_DSS, K_HALO_PACK, K_RK_COMBINE, K_DP3D_FROM_PS, K_STEP_INIT, K_HV_FIRST, K_HV_SECOND, K_HV_UPDATE,
+  K_EULER_DIVDP, K_EULER_QMINMAX, K_MINMAX, K_EULER_ADVECT, K_EULER_FDSS, K_EULER_TAVG, K_REMAP, K_UPDATE_Q,
+  K_TRANSPOSE, K_HOOK, K_COUNT
+};
+extern const char* const kernel_names[K_COUNT];
+
 struct DevConst {
   double dvv[NP][NP];
   double hyai[NLEV + 1], hybi[NLEV + 1];
@@ -111,6 +119,8 @@ struct Session {
   void* nccl = nullptr;  // ncclComm_t
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
+  int64_t launches_by[K_COUNT] = {};
+  unsigned long long profile_mask = 0;
   Params p{};
   DevConst hc{};  // host copy of the constants
   bool have_dvv = false, have_hv = false;
@@ -155,7 +165,18 @@ extern Session S;
 [[noreturn]] void runtime_abort(const char* msg, int code);
 void cuda_check(cudaError_t e, const char* what, const char* file, int line);
 #define CUDA_OK(x) ::hxx::cuda_check((x), #x, __FILE__, __LINE__)
-#define KERNEL_LAUNCHED() do { ++::hxx::S.launches; CUDA_OK(cudaGetLastError()); } while (0)
+// PROBE(id) before a launch and KERNEL_LAUNCHED(id) after it: launch accounting, error check and
+// (when the class is selected with hommexx_b200_profile) a CUDA-event pair on the launch stream.
+void probe_begin(int id);
+void probe_end(int id);
+#define PROBE(id) do { if (::hxx::S.profile_mask >> (id) & 1ull) ::hxx::probe_begin(id); } while (0)
+#define KERNEL_LAUNCHED(id)                                              \
+  do {                                                                   \
+    ++::hxx::S.launches;                                                 \
+    ++::hxx::S.launches_by[id];                                          \
+    CUDA_OK(cudaGetLastError());                                         \
+    if (::hxx::S.profile_mask >> (id) & 1ull) ::hxx::probe_end(id);      \
+  } while (0)
 
 // per-translation-unit constant bank (no relocatable device code: each TU owns a copy)
 void register_const_uploader(void (*fn)(const DevConst&));

@@ -26,6 +26,35 @@ void upload_constants() {
   CUDA_OK(cudaStreamSynchronize(S.stream));
 }
 
+const char* const kernel_names[K_COUNT] = {
+    "caar", "dss", "halo_pack", "rk_combine", "dp3d_from_ps", "prim_step_init", "hv_first_laplace",
+    "hv_second_laplace_pre_exchange", "hv_update_states", "euler_divdp", "euler_qminmax", "minmax",
+    "euler_advect", "euler_fdss", "euler_time_avg", "remap", "update_q", "transpose", "hook"};
+
+// ---- per-kernel CUDA-event probes (on the launch stream) -----------------------------------
+namespace {
+struct ProbePair { cudaEvent_t a, b; int id; };
+std::vector<ProbePair> g_probes;       // recorded pairs since the last reset
+std::vector<ProbePair> g_probe_pool;   // recycled events
+cudaEvent_t g_open[K_COUNT];
+cudaEvent_t g_marks[16];
+bool g_marks_made = false;
+}  // namespace
+
+void probe_begin(int id) {
+  ProbePair pp;
+  if (!g_probe_pool.empty()) { pp = g_probe_pool.back(); g_probe_pool.pop_back(); }
+  else { CUDA_OK(cudaEventCreate(&pp.a)); CUDA_OK(cudaEventCreate(&pp.b)); }
+  pp.id = id;
+  CUDA_OK(cudaEventRecord(pp.a, S.stream));
+  g_open[id] = pp.a;
+  g_probes.push_back(pp);
+}
+void probe_end(int id) {
+  for (auto it = g_probes.rbegin(); it != g_probes.rend(); ++it)
+    if (it->id == id && it->a == g_open[id]) { CUDA_OK(cudaEventRecord(it->b, S.stream)); return; }
+}
+
 void runtime_abort(const char* msg, int code) {
   // ErrorDefs.cpp:23-27 (MPI_Abort -> exit: one process per GPU, torchrun tears the job down)
   std::fprintf(stderr, "%s\nExiting...\n", msg);
@@ -76,8 +105,9 @@ __global__ void transpose_batched(const double* __restrict__ src, double* __rest
 static void launch_transpose(const double* src, double* dst, size_t nbatch, int R, int C) {
   if (!nbatch) return;
   const size_t smem = (size_t)R * (C + 1) * sizeof(double);
+  PROBE(K_TRANSPOSE);
   transpose_batched<<<(unsigned)nbatch, 256, smem, S.stream>>>(src, dst, R, C);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_TRANSPOSE);
 }
 
 constexpr size_t STAGE_BYTES = size_t(256) << 20;
@@ -244,6 +274,45 @@ void hommexx_b200_set_comm(int rank, int size, int device, const void* nccl_uniq
     runtime_abort("hommexx_b200: built without NCCL; multi-GPU runs are unavailable", 12);
 #endif
   }
+}
+
+void hommexx_b200_profile(unsigned long long mask) {
+  for (auto& p : g_probes) g_probe_pool.push_back(p);
+  g_probes.clear();
+  S.profile_mask = mask;
+  for (auto& c : S.launches_by) c = 0;
+}
+
+int hommexx_b200_kernel_id(const char* name) {
+  for (int i = 0; i < K_COUNT; ++i)
+    if (!std::strcmp(kernel_names[i], name)) return i;
+  return -1;
+}
+const char* hommexx_b200_kernel_name(int id) { return id >= 0 && id < K_COUNT ? kernel_names[id] : nullptr; }
+
+// total device milliseconds and launch count of one kernel class since hommexx_b200_profile()
+double hommexx_b200_profile_read(int id, int64_t* launches) {
+  if (S.stream) CUDA_OK(cudaStreamSynchronize(S.stream));
+  double ms = 0.0;
+  for (auto& p : g_probes)
+    if (p.id == id) {
+      float t = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&t, p.a, p.b));
+      ms += t;
+    }
+  if (launches) *launches = (id >= 0 && id < K_COUNT) ? S.launches_by[id] : 0;
+  return ms;
+}
+
+void hommexx_b200_event_record(int slot) {
+  if (!g_marks_made) { for (auto& e : g_marks) CUDA_OK(cudaEventCreate(&e)); g_marks_made = true; }
+  CUDA_OK(cudaEventRecord(g_marks[slot & 15], S.stream));
+}
+double hommexx_b200_event_elapsed_ms(int a, int b) {
+  float t = 0.f;
+  CUDA_OK(cudaEventSynchronize(g_marks[b & 15]));
+  CUDA_OK(cudaEventElapsedTime(&t, g_marks[a & 15], g_marks[b & 15]));
+  return t;
 }
 
 // ---- section A ----------------------------------------------------------------------------

@@ -32,7 +32,10 @@ __device__ __forceinline__ double integrate_parabola(double sq, double lin, doub
 
 // compute_partitions :506-597 + compute_integral_bounds :600-666 + compute_grids :366-413.
 // On entry c.dpo[PAD..] holds the source thickness and c.tgt the target thickness.
-__device__ void ppm_column_grids(ColSmem& c, int lane) {
+// Returns false when the target grid is not monotone (kid would leave the column): the reference
+// has undefined behaviour there; here the index is clamped and the caller raises the abort flag.
+__device__ bool ppm_column_grids(ColSmem& c, int lane) {
+  bool ok = true;
   if (lane == 0) {
     double acc = 0.0;
     for (int k = 0; k < NLEV; ++k) { c.pio[k] = acc; acc += c.dpo[k + PAD]; }
@@ -49,9 +52,10 @@ __device__ void ppm_column_grids(ColSmem& c, int lane) {
   __syncwarp();
   for (int k = lane; k < NLEV; k += 32) {
     int kk = k + 1;
-    while (c.pio[kk - 1] <= c.pin[k + 1]) kk++;
+    while (kk <= NLEV + 1 && c.pio[kk - 1] <= c.pin[k + 1]) kk++;
     kk--;
     if (kk == NLEV + 1) kk = NLEV;
+    if (kk < 1) { kk = 1; ok = false; }
     c.kid[k] = kk - 1;
     c.z2[k] = (c.pin[k + 1] - (c.pio[kk - 1] + c.pio[kk]) * 0.5) / c.dpo[kk + 1 + PAD - 2];
   }
@@ -71,6 +75,7 @@ __device__ void ppm_column_grids(ColSmem& c, int lane) {
     c.ppmdx[9][j] = dx[j + 2] * (dx[j + 2] + dx[j + 3]) / (dx[j + 1] + 2.0 * dx[j + 2]);
   }
   __syncwarp();
+  return !__any_sync(0xffffffffu, !ok);
 }
 
 // compute_remap_phase :203-266 for one field of the column; c.var holds the field (mass units)
@@ -152,7 +157,11 @@ __global__ void __launch_bounds__(RW * 32) remap_kernel(const RemapArgs a) {
     c.dpo[k + PAD] = s;
     bad |= (isnan(s) || s < 0.0);  // check_source_thickness :439-464
   }
-  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.invalid, 1);
+  if (__any_sync(0xffffffffu, bad)) {
+    // RemapFunctor.hpp:190-198: the run aborts after the launch; the column is left untouched
+    if (lane == 0) atomicOr(a.invalid, 1);
+    return;
+  }
   __syncwarp();
   // compute_ps_v :367-385 (serial sum, k ascending)
   double ps = 0.0;
@@ -165,7 +174,7 @@ __global__ void __launch_bounds__(RW * 32) remap_kernel(const RemapArgs a) {
   // compute_target_thickness :417-437
   for (int k = lane; k < NLEV; k += 32) c.tgt[k] = dc.dai[k] * dc.ps0 + dc.dbi[k] * ps;
   __syncwarp();
-  ppm_column_grids(c, lane);
+  if (!ppm_column_grids(c, lane) && lane == 0) atomicOr(a.invalid, 1);
   const int nf = 3 + a.qsize;
   for (int f = 0; f < nf; ++f) {
     double* fld = f == 0 ? a.v + off_v(ie, a.np1, 0) : f == 1 ? a.v + off_v(ie, a.np1, 1)
@@ -198,8 +207,9 @@ void vertical_remap(int np1, int np1_qdp) {
     attr = true;
   }
   const long long ncol = (long long)S.nelemd * NPSQ;
+  PROBE(K_REMAP);
   remap_kernel<<<(unsigned)((ncol + RW - 1) / RW), RW * 32, smem, S.stream>>>(a);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_REMAP);
 }
 
 void check_remap_flag() {
@@ -248,8 +258,9 @@ extern "C" void hxx_remap_columns(int alg, int ncols, int nfields, const double*
   CUDA_OK(cudaMemcpyAsync(d_f, fields, nfb, cudaMemcpyHostToDevice, S.stream));
   constexpr size_t smem = RW * sizeof(ColSmem);
   CUDA_OK(cudaFuncSetAttribute(remap_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PROBE(K_HOOK);
   remap_columns_kernel<<<(ncols + RW - 1) / RW, RW * 32, smem, S.stream>>>(alg, ncols, nfields, d_src, d_tgt, d_f);
-  KERNEL_LAUNCHED();
+  KERNEL_LAUNCHED(K_HOOK);
   CUDA_OK(cudaMemcpyAsync(fields, d_f, nfb, cudaMemcpyDeviceToHost, S.stream));
   CUDA_OK(cudaStreamSynchronize(S.stream));
   cudaFree(d_src); cudaFree(d_tgt); cudaFree(d_f);

@@ -114,6 +114,18 @@ int hommexx_b200_nccl_unique_id(void* out128);
 int64_t hommexx_b200_launch_count(void);
 /* Blocks until all device work issued so far has completed. */
 void hommexx_b200_sync(void);
+/* CUDA-event timing on the library's own launch stream (torch.cuda.Event only sees torch's
+ * stream): record into slot 0..15, elapsed milliseconds between two recorded slots. */
+void hommexx_b200_event_record(int slot);
+double hommexx_b200_event_elapsed_ms(int slot_a, int slot_b);
+/* Per-kernel probes: bit i of mask selects kernel class i (hommexx_b200_kernel_id("euler_advect"),
+ * ...); every launch of a selected class is bracketed by a CUDA-event pair. Calling it again
+ * resets the per-class launch counters and the recorded pairs. profile_read returns the summed
+ * device milliseconds of one class and its launch count since the last reset. */
+void hommexx_b200_profile(unsigned long long mask);
+int hommexx_b200_kernel_id(const char* name);
+const char* hommexx_b200_kernel_name(int id);
+double hommexx_b200_profile_read(int id, int64_t* launches);
 
 /* ------------------------------------------------------------------------------------------
  * C. Phase-level entry points: the public run methods of the reference's functors, exposed

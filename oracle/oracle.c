@@ -118,6 +118,12 @@ void hommexx_b200_set_comm(int rank, int size, int device, const void* id) {
 }
 int64_t hommexx_b200_launch_count(void) { return 0; }
 void hommexx_b200_sync(void) {}
+void hommexx_b200_event_record(int slot) { (void)slot; }
+double hommexx_b200_event_elapsed_ms(int a, int b) { (void)a; (void)b; return 0.0; }
+void hommexx_b200_profile(unsigned long long mask) { (void)mask; }
+int hommexx_b200_kernel_id(const char* name) { (void)name; return -1; }
+const char* hommexx_b200_kernel_name(int id) { (void)id; return NULL; }
+double hommexx_b200_profile_read(int id, int64_t* launches) { (void)id; if (launches) *launches = 0; return 0.0; }
 
 /* ------------------------------------------------------------------------------------------ */
 /* Session / init                                                                              */

