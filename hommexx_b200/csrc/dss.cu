@@ -33,8 +33,16 @@ static const int CORNER_PTS[4] = {0, 3, 12, 15};
 constexpr int NODES_PB = (NLEV * 4 <= 288) ? 4 : 2;  // nodes per block
 constexpr int DSS_FPB = 8;                           // fields per thread (grid.y chunks)
 
+#ifndef HXX_DSS_FB
+#define HXX_DSS_FB 1
+#endif
+#ifndef HXX_DSS_MINB
+#define HXX_DSS_MINB 5
+#endif
+constexpr int DSS_FB = HXX_DSS_FB;  // fields whose loads are in flight together in one thread
+
 template <bool RSP>
-__global__ void __launch_bounds__(NODES_PB* NLEV)
+__global__ void __launch_bounds__(NODES_PB* NLEV, HXX_DSS_MINB)
     dss_nodes_kernel(const DssNode* __restrict__ nodes, int nnodes, FieldList fl, const double* __restrict__ geo,
                      const double* __restrict__ halo) {
   const int nl = threadIdx.x / NLEV, k = threadIdx.x % NLEV;
@@ -46,36 +54,46 @@ __global__ void __launch_bounds__(NODES_PB* NLEV)
   for (int m = 0; m < 4; ++m)
     rs[m] = (RSP && m < nd.nmem && nd.src[m] >= 0) ? __ldg(geo + (size_t)nd.src[m] * GEO_N + G_RSPHEREMP) : 1.0;
   const int f0 = blockIdx.y * DSS_FPB, f1 = min(fl.nf, f0 + DSS_FPB);
-  for (int f = f0; f < f1; ++f) {
-    double* base = fl.base[f];
-    const long long es = fl.estride[f];
-    double val[4];
-    double* ptr[4];
+  for (int fb = f0; fb < f1; fb += DSS_FB) {
+    // the loads of DSS_FB fields are issued before the first store (the fields may alias as far
+    // as the compiler knows, which would otherwise serialise load -> store -> load)
+    double val[DSS_FB][4];
+    double* ptr[DSS_FB][4];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      val[m] = 0.0;
-      ptr[m] = nullptr;
-      if (m < nd.nmem) {
-        const int s = nd.src[m];
-        if (s >= 0) {
-          ptr[m] = base + (size_t)(s >> 4) * es + (s & 15) * NLEV + k;
-          val[m] = *ptr[m];
-        } else {
-          val[m] = halo[((size_t)(~s) * fl.nf + f) * NLEV + k];
+    for (int j = 0; j < DSS_FB; ++j) {
+      const int f = min(fb + j, f1 - 1);
+      double* base = fl.base[f];
+      const long long es = fl.estride[f];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        val[j][m] = 0.0;
+        ptr[j][m] = nullptr;
+        if (m < nd.nmem) {
+          const int s = nd.src[m];
+          if (s >= 0) {
+            ptr[j][m] = base + (size_t)(s >> 4) * es + (s & 15) * NLEV + k;
+            val[j][m] = *ptr[j][m];
+          } else {
+            val[j][m] = halo[((size_t)(~s) * fl.nf + f) * NLEV + k];
+          }
         }
       }
     }
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      if (ptr[m]) {
-        double acc = val[m];
+    for (int j = 0; j < DSS_FB; ++j) {
+      if (fb + j >= f1) break;
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-          const int o = nd.ord[m][t];
-          if (o < 4) acc += val[o];
+      for (int m = 0; m < 4; ++m) {
+        if (ptr[j][m]) {
+          double acc = val[j][m];
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            const int o = nd.ord[m][t];
+            if (o < 4) acc += o == 0 ? val[j][0] : o == 1 ? val[j][1] : o == 2 ? val[j][2] : val[j][3];
+          }
+          if (RSP) acc *= rs[m];
+          *ptr[j][m] = acc;
         }
-        if (RSP) acc *= rs[m];
-        *ptr[m] = acc;
       }
     }
   }

@@ -55,39 +55,75 @@ __global__ void __launch_bounds__(TPB, 2)
   plane_store(divdp_proj + off_f(ie) + k, div);
 }
 
+// ---- cp.async staging (LDGSTS): each thread streams the planes of the tracers it will process
+// into its own shared-memory slots two tracers ahead of the arithmetic, so HBM latency is hidden
+// behind the FP64 work of the current tracer without holding the in-flight data in registers.
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
 // compute_dp + compute_qmin_qmax (:406-485) and, on the hyperviscosity stage,
-// compute_biharmonic_pre (:196-214, dpdiss_adjustment :251-267): Q -> laplace(Q * dpdiss_ave / dp0)
-__global__ void __launch_bounds__(TPB, 2) euler_qminmax_kernel(const EulerArgs a) {
+// compute_biharmonic_pre (:196-214, dpdiss_adjustment :251-267): Q -> laplace(Q * dpdiss_ave / dp0).
+// The tracer planes are staged two tracers ahead with cp.async, as in the advection kernel.
+template <bool BIH>
+__global__ void __launch_bounds__(TPB, BIH ? 2 : 4) euler_qminmax_kernel(const EulerArgs a) {
+  extern __shared__ double s_all[];
   int ie, k;
   if (!map_thread(a.nelem, ie, k)) return;
+  double* const s_q = s_all + threadIdx.x;  // [2][16][TPB]
   const double* __restrict__ g = a.geo + (size_t)ie * NPSQ * GEO_N;
+  const int q0 = blockIdx.y * a.qchunk, q1 = min(a.qsize, q0 + a.qchunk);
+  const double* const qin = a.qdp + off_q(ie, a.n0_qdp, 0) + k;
+  auto prefetch = [&](int q, int buf) {
+    if (q < q1) {
+      const double* src = qin + (size_t)q * NLF;
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) cp_async8(s_q + (buf * NPSQ + p) * TPB, src + p * NLEV);
+    }
+    cp_async_commit();
+  };
+  prefetch(q0, 0);
+  prefetch(q0 + 1, 1);
   double dps[NPSQ], dave[NPSQ];
   {
-    const double* dd = a.derived_dp + off_f(ie) + k;
-    const double* dj = a.divdp_proj + off_f(ie) + k;
+    double r0[NPSQ], r1[NPSQ];
+    plane_load(a.derived_dp + off_f(ie) + k, r0);
+    plane_load(a.divdp_proj + off_f(ie) + k, r1);
     HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) dps[p] = dd[p * NLEV] - a.rhsmdt * dj[p * NLEV];
+    for (int p = 0; p < NPSQ; ++p) dps[p] = r0[p] - a.rhsmdt * r1[p];
   }
-  const bool bih = a.rhs_mode == 2;
-  if (bih && a.nu_p > 0) plane_load(a.dpdiss_ave + off_f(ie) + k, dave);
+  const bool scale = BIH && a.nu_p > 0;
+  if (scale) plane_load(a.dpdiss_ave + off_f(ie) + k, dave);
   const double dp0k = dc.dp0[k];
-  const int q0 = blockIdx.y * a.qchunk, q1 = min(a.qsize, q0 + a.qchunk);
-  for (int q = q0; q < q1; ++q) {
+  double* ql = a.qlim + ((size_t)ie * QSIZE_D + q0) * 2 * NLEV + k;
+  double* qtb = a.qtens_biharmonic + ((size_t)ie * QSIZE_D + q0) * NLF + k;
+  double mn_n = 0.0, mx_n = 0.0;
+  if (a.rhs_mode == 1) { mn_n = ql[0]; mx_n = ql[NLEV]; }
+  for (int q = q0; q < q1; ++q, ql += 2 * NLEV, qtb += NLF) {
+    const int buf = (q - q0) & 1;
+    double mn = mn_n, mx = mx_n;
+    if (a.rhs_mode == 1 && q + 1 < q1) { mn_n = ql[2 * NLEV]; mx_n = ql[3 * NLEV]; }
+    cp_async_wait<1>();
     double Q[NPSQ];
-    plane_load(a.qdp + off_q(ie, a.n0_qdp, q) + k, Q);
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) Q[p] = s_q[(buf * NPSQ + p) * TPB];
+    prefetch(q + 2, buf);
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) Q[p] = Q[p] / dps[p];
-    double* ql = a.qlim + ((size_t)ie * QSIZE_D + q) * 2 * NLEV + k;
-    double mn, mx;
     if (a.rhs_mode != 1) { mn = Q[0]; mx = Q[0]; }
-    else { mn = ql[0]; mx = ql[NLEV]; }
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) { mn = fmin(mn, Q[p]); mx = fmax(mx, Q[p]); }
     ql[0] = mn;
     ql[NLEV] = mx;
-    if (bih) {
+    if (BIH) {
       double lap[NPSQ];
-      if (a.nu_p > 0) {
+      if (scale) {
         HXX_UNROLL
         for (int p = 0; p < NPSQ; ++p) Q[p] = Q[p] * dave[p] / dp0k;
       }
@@ -95,24 +131,65 @@ __global__ void __launch_bounds__(TPB, 2) euler_qminmax_kernel(const EulerArgs a
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p)
         if (is_interior_pt(p)) lap[p] *= geo_ld(g, p, G_RSPHEREMP);  // rspheremp of the DSS that follows
-      plane_store(a.qtens_biharmonic + ((size_t)ie * QSIZE_D + q) * NLF + k, lap);
+      plane_store(qtb, lap);
     }
   }
+  cp_async_wait<0>();
 }
+
+// shared-memory doubles per thread: vstar (2x16), dpdissk (16), 2 staged qdp planes (2x16) and,
+// on the hyperviscosity stage, 2 staged qtens_biharmonic planes (2x16); slot s of thread t lives
+// at [s][t], so a warp's access to one slot is 256 contiguous bytes (conflict-free).
+#ifndef HXX_ADV_STAGES
+#define HXX_ADV_STAGES 1
+#endif
+#ifndef HXX_ADV_MINB
+#define HXX_ADV_MINB 3
+#endif
+#ifndef HXX_ADV_MINB_HV
+#define HXX_ADV_MINB_HV 2
+#endif
+constexpr int ADV_NST = HXX_ADV_STAGES;  // staged tracers in flight per thread
+template <bool HV>
+constexpr int advect_slots() { return 48 + NPSQ * ADV_NST * (HV ? 2 : 1); }
 
 // advect_and_limit :317-332 = compute_2d_advection_step (:585-626) + run_tracer_phase (:571-582),
 // with compute_biharmonic_post (:216-231, rhsviss_adjustment :293-310) applied on the fly.
-__global__ void __launch_bounds__(TPB, 2) euler_advect_kernel(const EulerArgs a) {
-  extern __shared__ double s_vs[];  // vstar: [2][16][blockDim] thread-private slots
+template <bool HV>
+__global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) euler_advect_kernel(const EulerArgs a) {
+  extern __shared__ double s_all[];
   int ie, k;
-  if (!map_thread(a.nelem, ie, k)) return;
-  const int nt = TPB, tid = threadIdx.x;
+  if (!map_thread(a.nelem, ie, k)) return;  // no block-wide barrier below: early exit is safe
+  const int tid = threadIdx.x;
+  double* const s_vs0 = s_all + tid;
+  double* const s_vs1 = s_all + 16 * TPB + tid;
+  double* const s_dpk = s_all + 32 * TPB + tid;
+  double* const s_q = s_all + 48 * TPB + tid;
+  double* const s_b = s_all + (48 + NPSQ * ADV_NST) * TPB + tid;
   const double* __restrict__ g = a.geo + (size_t)ie * NPSQ * GEO_N;
   const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
-  const bool add_hv = a.rhs_viss != 0.0;
-  const bool add_ps_diss = a.nu_p > 0 && add_hv;
+  const int q0 = blockIdx.y * a.qchunk, q1 = min(a.qsize, q0 + a.qchunk);
+  const double* const qin = a.qdp + off_q(ie, a.n0_qdp, 0) + k;
+  const double* const qtb = a.qtens_biharmonic + (size_t)ie * QSIZE_D * NLF + k;
+  auto prefetch = [&](int q, int buf) {
+    if (q < q1) {
+      const double* src = qin + (size_t)q * NLF;
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) cp_async8(s_q + (buf * NPSQ + p) * TPB, src + p * NLEV);
+      if (HV) {
+        const double* sb = qtb + (size_t)q * NLF;
+        HXX_UNROLL
+        for (int p = 0; p < NPSQ; ++p) cp_async8(s_b + (buf * NPSQ + p) * TPB, sb + p * NLEV);
+      }
+    }
+    cp_async_commit();  // possibly empty: keeps one group per loop iteration
+  };
+  HXX_UNROLL
+  for (int i = 0; i < ADV_NST; ++i) prefetch(q0 + i, i);
+
+  const bool add_ps_diss = a.nu_p > 0 && HV;
   const double diss_fac = add_ps_diss ? -a.rhs_viss * a.dt * a.nu_q : 0.0;
-  double dpk[NPSQ], c[NPSQ];
+  double c[NPSQ];
   {
     const double* dd = a.derived_dp + off_f(ie) + k;
     const double* dj = a.divdp_proj + off_f(ie) + k;
@@ -120,41 +197,60 @@ __global__ void __launch_bounds__(TPB, 2) euler_advect_kernel(const EulerArgs a)
     const double* n0 = a.derived_vn0 + ((size_t)ie * 2 + 0) * NLF + k;
     const double* n1 = a.derived_vn0 + ((size_t)ie * 2 + 1) * NLF + k;
     const double* db = a.dpdiss_biharmonic + off_f(ie) + k;
+    double r0[NPSQ], r1[NPSQ], r2[NPSQ], r3[NPSQ], r4[NPSQ], r5[NPSQ];
+    plane_load(dd, r0);
+    plane_load(dj, r1);
+    plane_load(dv, r2);
+    plane_load(n0, r3);
+    plane_load(n1, r4);
+    if (add_ps_diss) plane_load(db, r5);
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {
       const double sm_ = geo_ld(g, p, G_SPHEREMP);
-      const double dp = dd[p * NLEV] - a.rhsmdt * dj[p * NLEV];
-      s_vs[(0 * NPSQ + p) * nt + tid] = n0[p * NLEV] / dp;
-      s_vs[(1 * NPSQ + p) * nt + tid] = n1[p * NLEV] / dp;
-      double d = dp - a.dt * dv[p * NLEV];
-      if (add_ps_diss) d += diss_fac * db[p * NLEV] / sm_;
-      dpk[p] = d;
+      const double dp = r0[p] - a.rhsmdt * r1[p];
+      s_vs0[p * TPB] = r3[p] / dp;
+      s_vs1[p * TPB] = r4[p] / dp;
+      double d = dp - a.dt * r2[p];
+      if (add_ps_diss) d += diss_fac * r5[p] / sm_;
+      s_dpk[p * TPB] = d;
       c[p] = sm_ * d;
     }
   }
   if (blockIdx.y == 0 && a.f_dss) {  // f_dss *= spheremp (and the interior part of the DSS rspheremp)
     double* f = a.f_dss + off_f(ie) + k;
+    double r[NPSQ];
+    plane_load(f, r);
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {
-      double r = f[p * NLEV] * geo_ld(g, p, G_SPHEREMP);
-      if (is_interior_pt(p)) r *= geo_ld(g, p, G_RSPHEREMP);
-      f[p * NLEV] = r;
+      r[p] = r[p] * geo_ld(g, p, G_SPHEREMP);
+      if (is_interior_pt(p)) r[p] *= geo_ld(g, p, G_RSPHEREMP);
     }
+    plane_store(f, r);
   }
   const double dp0k = dc.dp0[k];
   const double bfac = -a.rhs_viss * a.dt * a.nu_q;
   const double alpha = -a.dt;
-  const int q0 = blockIdx.y * a.qchunk, q1 = min(a.qsize, q0 + a.qchunk);
-  for (int q = q0; q < q1; ++q) {
+  double* qlp = a.qlim + ((size_t)ie * QSIZE_D + q0) * 2 * NLEV + k;
+  double* out = a.qdp + off_q(ie, a.np1_qdp, q0) + k;
+  double qmin_n = qlp[0], qmax_n = qlp[NLEV];
+  for (int q = q0; q < q1; ++q, qlp += 2 * NLEV, out += NLF) {
+    const int buf = (q - q0) % ADV_NST;
+    const double qmin0 = qmin_n, qmax0 = qmax_n;
+    if (q + 1 < q1) {  // next tracer's bounds, loaded a whole iteration early
+      qmin_n = qlp[2 * NLEV];
+      qmax_n = qlp[3 * NLEV];
+    }
+    cp_async_wait<ADV_NST - 1>();  // this thread's copies of tracer q have landed
     double x[NPSQ];
     {
       double qd[NPSQ], gv0[NPSQ], gv1[NPSQ];
-      plane_load(a.qdp + off_q(ie, a.n0_qdp, q) + k, qd);
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) qd[p] = s_q[(buf * NPSQ + p) * TPB];
       // divergence_sphere_update, SphereOperators.hpp:398-444
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) {
-        const double u = s_vs[(0 * NPSQ + p) * nt + tid] * qd[p];
-        const double v = s_vs[(1 * NPSQ + p) * nt + tid] * qd[p];
+        const double u = s_vs0[p * TPB] * qd[p];
+        const double v = s_vs1[p * TPB] * qd[p];
         const double md = geo_ld(g, p, G_METDET);
         gv0[p] = (geo_ld(g, p, G_DINV00) * u + geo_ld(g, p, G_DINV10) * v) * md;
         gv1[p] = (geo_ld(g, p, G_DINV01) * u + geo_ld(g, p, G_DINV11) * v) * md;
@@ -164,34 +260,38 @@ __global__ void __launch_bounds__(TPB, 2) euler_advect_kernel(const EulerArgs a)
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) x[p] = qd[p] + alpha * ((dx[p] + dy[p]) * geo_ld(g, p, G_RMETDET_R));
     }
-    if (add_hv) {
+    if (HV) {
+      // x is parked in the (already consumed) qdp staging slot while the Laplacian needs registers
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) s_q[(buf * NPSQ + p) * TPB] = x[p];
       double s[NPSQ], lap[NPSQ];
-      plane_load(a.qtens_biharmonic + ((size_t)ie * QSIZE_D + q) * NLF + k, s);
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) s[p] = s_b[(buf * NPSQ + p) * TPB];
       if (a.consthv) laplace_simple(g, s, lap); else laplace_tensor(g, tv, s, lap);
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) x[p] += bfac * dp0k * lap[p] / geo_ld(g, p, G_SPHEREMP);
+      for (int p = 0; p < NPSQ; ++p)
+        x[p] = s_q[(buf * NPSQ + p) * TPB] + bfac * dp0k * lap[p] / geo_ld(g, p, G_SPHEREMP);
     }
+    prefetch(q + ADV_NST, buf);  // the staged planes of tracer q are in registers now: refill the slot
     // limiter shell :693-761
-    double* ql = a.qlim + ((size_t)ie * QSIZE_D + q) * 2 * NLEV + k;
-    double qmin = ql[0], qmax = ql[NLEV];
-    const double qmin0 = qmin, qmax0 = qmax;
+    double qmin = qmin0, qmax = qmax0;
     double xs[NPSQ];
     HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) xs[p] = x[p] / dpk[p];
+    for (int p = 0; p < NPSQ; ++p) xs[p] = x[p] / s_dpk[p * TPB];
     if (limiter_level(a.limiter_option, c, xs, qmin, qmax)) {
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) x[p] = xs[p] * dpk[p];
-      if (qmin != qmin0) ql[0] = qmin;
-      if (qmax != qmax0) ql[NLEV] = qmax;
+      for (int p = 0; p < NPSQ; ++p) x[p] = xs[p] * s_dpk[p * TPB];
+      if (qmin != qmin0) qlp[0] = qmin;
+      if (qmax != qmax0) qlp[NLEV] = qmax;
     }
-    double* out = a.qdp + off_q(ie, a.np1_qdp, q) + k;  // apply_spheremp :672-687
     HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) {
+    for (int p = 0; p < NPSQ; ++p) {  // apply_spheremp :672-687
       double r = geo_ld(g, p, G_SPHEREMP) * x[p];
       if (is_interior_pt(p)) r *= geo_ld(g, p, G_RSPHEREMP);
       out[p * NLEV] = r;
     }
   }
+  cp_async_wait<0>();
 }
 
 // f_dss *= spheremp on its own, for the one case where the advection kernel still reads it
@@ -228,7 +328,7 @@ static int tracer_chunk() {
   static int qc = 0;
   if (!qc) {
     const char* e = std::getenv("HXX_QCHUNK");
-    qc = e ? std::max(1, std::atoi(e)) : 10;
+    qc = e ? std::max(1, std::atoi(e)) : 20;
   }
   return qc;
 }
@@ -244,7 +344,11 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
               S.p.consthv ? 1 : 0};
   const dim3 grid(nblocks_flat(S.nelemd), (nq + a.qchunk - 1) / a.qchunk);
   PROBE(K_EULER_QMINMAX);
-  euler_qminmax_kernel<<<grid, TPB, 0, S.stream>>>(a);
+  {
+    constexpr size_t smem_mm = 2 * (size_t)NPSQ * TPB * sizeof(double);
+    if (mode == 2) euler_qminmax_kernel<true><<<grid, TPB, smem_mm, S.stream>>>(a);
+    else euler_qminmax_kernel<false><<<grid, TPB, smem_mm, S.stream>>>(a);
+  }
   KERNEL_LAUNCHED(K_EULER_QMINMAX);
   if (mode == 0) {
     minmax_exchange();  // neighbor_minmax :504-507
@@ -255,10 +359,14 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
     minmax_exchange();
   }
   a.qlim = S.qlim;  // minmax_exchange swaps the double buffer
-  constexpr size_t smem = 2 * (size_t)NPSQ * TPB * sizeof(double);
+  const bool hv = S.rhs_viss != 0.0;
+  const size_t smem = (size_t)(hv ? advect_slots<true>() : advect_slots<false>()) * TPB * sizeof(double);
   static bool attr = false;
   if (!attr) {
-    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 advect_slots<true>() * TPB * (int)sizeof(double)));
+    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 advect_slots<false>() * TPB * (int)sizeof(double)));
     attr = true;
   }
   // divdp_proj is both the DSS variable of stage 1 and an input of compute_dp: scale it inside
@@ -267,7 +375,8 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   const bool separate = (fdss == S.divdp_proj && a.rhsmdt != 0.0);
   if (separate) a.f_dss = nullptr;
   PROBE(K_EULER_ADVECT);
-  euler_advect_kernel<<<grid, TPB, smem, S.stream>>>(a);
+  if (hv) euler_advect_kernel<true><<<grid, TPB, smem, S.stream>>>(a);
+  else euler_advect_kernel<false><<<grid, TPB, smem, S.stream>>>(a);
   KERNEL_LAUNCHED(K_EULER_ADVECT);
   if (separate) {
     PROBE(K_EULER_FDSS);

@@ -21,7 +21,11 @@ ORACLE_LIB = ROOT / "oracle" / "liboracle.so"
 
 
 def cuda_lib_path(nlev: int, qsize_d: int) -> pathlib.Path:
-    return PKG / "csrc" / f"libhommexx_b200_nlev{nlev}_q{qsize_d}.so"
+    # HXX_VARIANT selects an experimental build of the same sources (scripts/build_variant.py);
+    # unset = the product library
+    var = os.environ.get("HXX_VARIANT", "")
+    base = PKG / "csrc" / "variants" / var if var else PKG / "csrc"
+    return base / f"libhommexx_b200_nlev{nlev}_q{qsize_d}.so"
 
 
 class HommeParams(C.Structure):
