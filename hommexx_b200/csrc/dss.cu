@@ -41,7 +41,7 @@ constexpr int DSS_FPB = 8;                           // fields per thread (grid.
 #endif
 constexpr int DSS_FB = HXX_DSS_FB;  // fields whose loads are in flight together in one thread
 
-template <bool RSP>
+template <bool RSP, bool AVG>
 __global__ void __launch_bounds__(NODES_PB* NLEV, HXX_DSS_MINB)
     dss_nodes_kernel(const DssNode* __restrict__ nodes, int nnodes, FieldList fl, const double* __restrict__ geo,
                      const double* __restrict__ halo) {
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(NODES_PB* NLEV, HXX_DSS_MINB)
   for (int fb = f0; fb < f1; fb += DSS_FB) {
     // the loads of DSS_FB fields are issued before the first store (the fields may alias as far
     // as the compiler knows, which would otherwise serialise load -> store -> load)
-    double val[DSS_FB][4];
+    double val[DSS_FB][4], avg[DSS_FB][4];
     double* ptr[DSS_FB][4];
 #pragma unroll
     for (int j = 0; j < DSS_FB; ++j) {
@@ -67,12 +67,14 @@ __global__ void __launch_bounds__(NODES_PB* NLEV, HXX_DSS_MINB)
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         val[j][m] = 0.0;
+        avg[j][m] = 0.0;
         ptr[j][m] = nullptr;
         if (m < nd.nmem) {
           const int s = nd.src[m];
           if (s >= 0) {
             ptr[j][m] = base + (size_t)(s >> 4) * es + (s & 15) * NLEV + k;
             val[j][m] = *ptr[j][m];
+            avg[j][m] = (AVG && f < fl.navg) ? ptr[j][m][fl.avg_delta] : 0.0;
           } else {
             val[j][m] = halo[((size_t)(~s) * fl.nf + f) * NLEV + k];
           }
@@ -92,7 +94,131 @@ __global__ void __launch_bounds__(NODES_PB* NLEV, HXX_DSS_MINB)
             if (o < 4) acc += o == 0 ? val[j][0] : o == 1 ? val[j][1] : o == 2 ? val[j][2] : val[j][3];
           }
           if (RSP) acc *= rs[m];
+          if (AVG && fb + j < fl.navg) acc = (avg[j][m] + 2.0 * acc) / 3.0;  // qdp_time_avg, EulerStepFunctorImpl.hpp:379-403
           *ptr[j][m] = acc;
+        }
+      }
+    }
+  }
+}
+
+// ---- lean paths -------------------------------------------------------------------------------
+// 80 % of the boundary nodes are edge nodes with two on-rank sharers and nearly all the others
+// are regular element corners with four: they get branch-free kernels with a handful of
+// instructions per (node, level, field). What is left (cube vertices with three sharers, nodes
+// with a sharer on another rank) goes through the generic kernel above.
+//
+// Pair: both results are a + b (addition commutes, so the reference's "own value first" order
+// gives the same bits for both members).
+// Quad: members are stored in a canonical order (0; 1 = its W/E-edge neighbour; 2 = its
+// S/N-edge neighbour; 3 = the diagonal one), so member 0 always sums as ((v0 + v2) + v1) + v3
+// (unpack order BoundaryExchange.cpp:512-524: S/N edge, W/E edge, corner) and each other member
+// needs one bit saying which of its two edge neighbours comes first (it differs where the
+// element-local axes rotate across cube edges).
+struct DssPair { int a, b; };
+struct DssQuad { int m[4]; int swaps; int pad[3]; };
+static_assert(sizeof(DssQuad) == 32, "DssQuad layout");
+constexpr int DSS_TPB = 128;
+
+template <bool RSP, bool AVG>
+__global__ void __launch_bounds__(DSS_TPB)
+    dss_pair_kernel(const DssPair* __restrict__ pairs, int npairs, FieldList fl, const double* __restrict__ geo) {
+  const long long g = (long long)blockIdx.x * DSS_TPB + threadIdx.x;
+  const int ip = (int)(g / NLEV), k = (int)(g % NLEV);
+  if (ip >= npairs) return;
+  const DssPair pr = pairs[ip];
+  const long long ea = pr.a >> 4, eb = pr.b >> 4;
+  const int ca = (pr.a & 15) * NLEV + k, cb = (pr.b & 15) * NLEV + k;
+  double ra = 1.0, rb = 1.0;
+  if (RSP) {
+    ra = __ldg(geo + (size_t)pr.a * GEO_N + G_RSPHEREMP);
+    rb = __ldg(geo + (size_t)pr.b * GEO_N + G_RSPHEREMP);
+  }
+  const int f0 = blockIdx.y * DSS_FPB, f1 = min(fl.nf, f0 + DSS_FPB);
+  constexpr int UB = 4;  // fields whose loads are issued before the first store
+  for (int fb = f0; fb < f1; fb += UB) {
+    double *pa[UB], *pb[UB];
+    double va[UB], vb[UB], qa[UB], qb[UB];
+#pragma unroll
+    for (int j = 0; j < UB; ++j) {
+      const int f = min(fb + j, f1 - 1);
+      double* base = fl.base[f];
+      const long long es = fl.estride[f];
+      pa[j] = base + ea * es + ca;
+      pb[j] = base + eb * es + cb;
+      va[j] = *pa[j];
+      vb[j] = *pb[j];
+      if (AVG) {
+        qa[j] = f < fl.navg ? pa[j][fl.avg_delta] : 0.0;
+        qb[j] = f < fl.navg ? pb[j][fl.avg_delta] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < UB; ++j) {
+      if (fb + j < f1) {
+        const double s = va[j] + vb[j];
+        double xa = s, xb = s;
+        if (RSP) { xa = s * ra; xb = s * rb; }
+        if (AVG && fb + j < fl.navg) {  // qdp_time_avg, EulerStepFunctorImpl.hpp:379-403
+          xa = (qa[j] + 2.0 * xa) / 3.0;
+          xb = (qb[j] + 2.0 * xb) / 3.0;
+        }
+        *pa[j] = xa;
+        *pb[j] = xb;
+      }
+    }
+  }
+}
+
+template <bool RSP, bool AVG>
+__global__ void __launch_bounds__(DSS_TPB)
+    dss_quad_kernel(const DssQuad* __restrict__ quads, int nquads, FieldList fl, const double* __restrict__ geo) {
+  const long long g = (long long)blockIdx.x * DSS_TPB + threadIdx.x;
+  const int iq = (int)(g / NLEV), k = (int)(g % NLEV);
+  if (iq >= nquads) return;
+  const DssQuad qd = quads[iq];
+  long long e[4];
+  int c[4];
+  double rs[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    e[m] = qd.m[m] >> 4;
+    c[m] = (qd.m[m] & 15) * NLEV + k;
+    rs[m] = RSP ? __ldg(geo + (size_t)qd.m[m] * GEO_N + G_RSPHEREMP) : 1.0;
+  }
+  const bool s1 = qd.swaps & 1, s2 = qd.swaps & 2, s3 = qd.swaps & 4;
+  const int f0 = blockIdx.y * DSS_FPB, f1 = min(fl.nf, f0 + DSS_FPB);
+  constexpr int UB = 2;
+  for (int fb = f0; fb < f1; fb += UB) {
+    double* ptr[UB][4];
+    double v[UB][4], qa[UB][4];
+#pragma unroll
+    for (int j = 0; j < UB; ++j) {
+      const int f = min(fb + j, f1 - 1);
+      double* base = fl.base[f];
+      const long long es = fl.estride[f];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        ptr[j][m] = base + e[m] * es + c[m];
+        v[j][m] = *ptr[j][m];
+        if (AVG) qa[j][m] = f < fl.navg ? ptr[j][m][fl.avg_delta] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < UB; ++j) {
+      if (fb + j < f1) {
+        const double v0 = v[j][0], v1 = v[j][1], v2 = v[j][2], v3 = v[j][3];
+        double x[4];
+        x[0] = ((v0 + v2) + v1) + v3;
+        x[1] = s1 ? ((v1 + v0) + v3) + v2 : ((v1 + v3) + v0) + v2;
+        x[2] = s2 ? ((v2 + v3) + v0) + v1 : ((v2 + v0) + v3) + v1;
+        x[3] = s3 ? ((v3 + v2) + v1) + v0 : ((v3 + v1) + v2) + v0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          double r = x[m];
+          if (RSP) r *= rs[m];
+          if (AVG && fb + j < fl.navg) r = (qa[j][m] + 2.0 * r) / 3.0;
+          *ptr[j][m] = r;
         }
       }
     }
@@ -160,6 +286,9 @@ struct UF {
 
 void free_exchange_plan() {
   if (S.nodes) { cudaFree(S.nodes); S.nodes = nullptr; }
+  if (S.dss_pairs) { cudaFree(S.dss_pairs); S.dss_pairs = nullptr; }
+  if (S.dss_quads) { cudaFree(S.dss_quads); S.dss_quads = nullptr; }
+  S.npairs = S.nquads = 0;
   if (S.nbr8) { cudaFree(S.nbr8); S.nbr8 = nullptr; }
   if (S.send_src) { cudaFree(S.send_src); S.send_src = nullptr; }
   if (S.send_conn_elem) { cudaFree(S.send_conn_elem); S.send_conn_elem = nullptr; }
@@ -309,10 +438,61 @@ void build_exchange_plan() {
       nodes[nid].ord[me][t] = (uint8_t)(std::find(mem.begin(), mem.end(), id) - mem.begin());
     }
   }
-  S.nnodes = (int)nodes.size();
+  // -- split into the lean pair / quad lists and the generic remainder
+  std::vector<DssPair> pairs;
+  std::vector<DssQuad> quads;
+  std::vector<DssNode> rest;
+  for (const DssNode& nd : nodes) {
+    bool local = true;
+    for (int m = 0; m < nd.nmem; ++m) local = local && nd.src[m] >= 0;
+    if (local && nd.nmem == 2 && nd.ord[0][0] == 1 && nd.ord[0][1] == 255 && nd.ord[1][0] == 0 && nd.ord[1][1] == 255) {
+      pairs.push_back({nd.src[0], nd.src[1]});
+      continue;
+    }
+    if (local && nd.nmem == 4 && nd.ord[0][2] < 4) {
+      // canonical order: C0 = member 0, C2 = its first (S/N) neighbour, C1 = its second (W/E), C3 = diagonal
+      const int C[4] = {0, nd.ord[0][1], nd.ord[0][0], nd.ord[0][2]};
+      int inv[4] = {-1, -1, -1, -1};
+      bool okp = true;
+      for (int i = 0; i < 4; ++i) { if (C[i] > 3 || inv[C[i]] >= 0) okp = false; else inv[C[i]] = i; }
+      int swaps = 0;
+      if (okp) {
+        // expected (first, second, diag) of canonical members 1..3 and the swapped alternative
+        static const int expect[4][3] = {{2, 1, 3}, {3, 0, 2}, {0, 3, 1}, {1, 2, 0}};
+        for (int i = 1; i < 4 && okp; ++i) {
+          const uint8_t* o = nd.ord[C[i]];
+          if (o[0] > 3 || o[1] > 3 || o[2] > 3) { okp = false; break; }
+          const int a0 = inv[o[0]], a1 = inv[o[1]], a2 = inv[o[2]];
+          if (a2 != expect[i][2]) okp = false;
+          else if (a0 == expect[i][0] && a1 == expect[i][1]) {}
+          else if (a0 == expect[i][1] && a1 == expect[i][0]) swaps |= 1 << (i - 1);
+          else okp = false;
+        }
+      }
+      if (okp) {
+        DssQuad q{};
+        for (int i = 0; i < 4; ++i) q.m[i] = nd.src[C[i]];
+        q.swaps = swaps;
+        quads.push_back(q);
+        continue;
+      }
+    }
+    rest.push_back(nd);
+  }
+  S.nnodes = (int)rest.size();
+  S.npairs = (int)pairs.size();
+  S.nquads = (int)quads.size();
   if (S.nnodes) {
-    CUDA_OK(cudaMalloc(&S.nodes, nodes.size() * sizeof(DssNode)));
-    CUDA_OK(cudaMemcpy(S.nodes, nodes.data(), nodes.size() * sizeof(DssNode), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&S.nodes, rest.size() * sizeof(DssNode)));
+    CUDA_OK(cudaMemcpy(S.nodes, rest.data(), rest.size() * sizeof(DssNode), cudaMemcpyHostToDevice));
+  }
+  if (S.npairs) {
+    CUDA_OK(cudaMalloc(&S.dss_pairs, pairs.size() * sizeof(DssPair)));
+    CUDA_OK(cudaMemcpy(S.dss_pairs, pairs.data(), pairs.size() * sizeof(DssPair), cudaMemcpyHostToDevice));
+  }
+  if (S.nquads) {
+    CUDA_OK(cudaMalloc(&S.dss_quads, quads.size() * sizeof(DssQuad)));
+    CUDA_OK(cudaMemcpy(S.dss_quads, quads.data(), quads.size() * sizeof(DssQuad), cudaMemcpyHostToDevice));
   }
   // -- neighbour table for the min/max exchange
   std::vector<int> nbr8((size_t)n * 8, DSS_NONE);
@@ -360,12 +540,30 @@ void dss_exchange(const FieldList& fl, bool rspheremp) {
     KERNEL_LAUNCHED(K_HALO_PACK);
     halo_sendrecv(S.peer_send_off, S.peer_send_cnt, S.peer_recv_off, S.peer_recv_cnt, (size_t)fl.nf * NLEV);
   }
-  if (!S.nnodes) return;
-  const dim3 grid((S.nnodes + NODES_PB - 1) / NODES_PB, (fl.nf + DSS_FPB - 1) / DSS_FPB);
-  PROBE(K_DSS);
-  if (rspheremp) dss_nodes_kernel<true><<<grid, NODES_PB * NLEV, 0, S.stream>>>(S.nodes, S.nnodes, fl, S.geo, S.recvbuf);
-  else dss_nodes_kernel<false><<<grid, NODES_PB * NLEV, 0, S.stream>>>(S.nodes, S.nnodes, fl, S.geo, S.recvbuf);
-  KERNEL_LAUNCHED(K_DSS);
+  const int ny = (fl.nf + DSS_FPB - 1) / DSS_FPB;
+  const bool avg = fl.navg > 0;
+#define HXX_DSS_LAUNCH(KERNEL, GRID, BLOCK, ...)                                             \
+  do {                                                                                       \
+    PROBE(K_DSS);                                                                            \
+    if (avg && rspheremp) KERNEL<true, true><<<GRID, BLOCK, 0, S.stream>>>(__VA_ARGS__);     \
+    else if (avg) KERNEL<false, true><<<GRID, BLOCK, 0, S.stream>>>(__VA_ARGS__);            \
+    else if (rspheremp) KERNEL<true, false><<<GRID, BLOCK, 0, S.stream>>>(__VA_ARGS__);      \
+    else KERNEL<false, false><<<GRID, BLOCK, 0, S.stream>>>(__VA_ARGS__);                    \
+    KERNEL_LAUNCHED(K_DSS);                                                                  \
+  } while (0)
+  if (S.npairs) {
+    const dim3 grid((unsigned)(((long long)S.npairs * NLEV + DSS_TPB - 1) / DSS_TPB), ny);
+    HXX_DSS_LAUNCH(dss_pair_kernel, grid, DSS_TPB, (const DssPair*)S.dss_pairs, S.npairs, fl, S.geo);
+  }
+  if (S.nquads) {
+    const dim3 grid((unsigned)(((long long)S.nquads * NLEV + DSS_TPB - 1) / DSS_TPB), ny);
+    HXX_DSS_LAUNCH(dss_quad_kernel, grid, DSS_TPB, (const DssQuad*)S.dss_quads, S.nquads, fl, S.geo);
+  }
+  if (S.nnodes) {
+    const dim3 grid((S.nnodes + NODES_PB - 1) / NODES_PB, ny);
+    HXX_DSS_LAUNCH(dss_nodes_kernel, grid, NODES_PB * NLEV, S.nodes, S.nnodes, fl, S.geo, S.recvbuf);
+  }
+#undef HXX_DSS_LAUNCH
 }
 
 void scale_interior_rspheremp(const FieldList& fl) {
@@ -412,8 +610,12 @@ FieldList fields_hv() {  // HyperviscosityFunctorImpl.cpp:44-54
 double* dss_var(int dss_opt) {
   return dss_opt == DSS_ETA ? S.eta_dot_dpdn : dss_opt == DSS_OMEGA ? S.omega_p : S.divdp_proj;
 }
-FieldList fields_euler(int tq, int dss_opt) {  // EulerStepFunctorImpl.hpp:137-153
+FieldList fields_euler(int tq, int dss_opt, int tavg_n0_qdp) {  // EulerStepFunctorImpl.hpp:137-153
   FieldList f;
+  if (tavg_n0_qdp >= 0) {
+    f.navg = S.p.qsize;
+    f.avg_delta = (long long)off_q(0, tavg_n0_qdp, 0) - (long long)off_q(0, tq, 0);
+  }
   const int nq = S.p.qsize;
   f.nf = nq + 1;
   for (int q = 0; q < nq; ++q) { f.base[q] = S.qdp + off_q(0, tq, q); f.estride[q] = (long long)QNTL * QSIZE_D * NLF; }

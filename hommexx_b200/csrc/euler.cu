@@ -28,6 +28,7 @@ struct EulerArgs {
   int nelem, qsize, qchunk, n0_qdp, np1_qdp;
   double dt, rhsmdt, nu_p, nu_q, rhs_viss;
   int rhs_mode;  // 0, 1, 2 = rhs_multiplier
+  int tavg_n0;   // >= 0: fuse qdp_time_avg with this qdp time level (interior points here, boundary in the DSS)
   int limiter_option, consthv;
 };
 
@@ -53,19 +54,6 @@ __global__ void __launch_bounds__(TPB, 2)
   divergence_sphere(g, v0, v1, div);
   plane_store(divdp + off_f(ie) + k, div);
   plane_store(divdp_proj + off_f(ie) + k, div);
-}
-
-// ---- cp.async staging (LDGSTS): each thread streams the planes of the tracers it will process
-// into its own shared-memory slots two tracers ahead of the arithmetic, so HBM latency is hidden
-// behind the FP64 work of the current tracer without holding the in-flight data in registers.
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
 // compute_dp + compute_qmin_qmax (:406-485) and, on the hyperviscosity stage,
@@ -155,7 +143,7 @@ constexpr int advect_slots() { return 48 + NPSQ * ADV_NST * (HV ? 2 : 1); }
 
 // advect_and_limit :317-332 = compute_2d_advection_step (:585-626) + run_tracer_phase (:571-582),
 // with compute_biharmonic_post (:216-231, rhsviss_adjustment :293-310) applied on the fly.
-template <bool HV>
+template <bool HV, bool TAVG>
 __global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) euler_advect_kernel(const EulerArgs a) {
   extern __shared__ double s_all[];
   int ie, k;
@@ -240,6 +228,11 @@ __global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eule
       qmin_n = qlp[2 * NLEV];
       qmax_n = qlp[3 * NLEV];
     }
+    double qa[4] = {0.0, 0.0, 0.0, 0.0};
+    if (TAVG) {  // qdp_time_avg :379-403 partner values of the 4 interior points
+      const double* pa = a.qdp + off_q(ie, a.tavg_n0, q) + k;
+      qa[0] = pa[5 * NLEV]; qa[1] = pa[6 * NLEV]; qa[2] = pa[9 * NLEV]; qa[3] = pa[10 * NLEV];
+    }
     cp_async_wait<ADV_NST - 1>();  // this thread's copies of tracer q have landed
     double x[NPSQ];
     {
@@ -287,7 +280,10 @@ __global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eule
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {  // apply_spheremp :672-687
       double r = geo_ld(g, p, G_SPHEREMP) * x[p];
-      if (is_interior_pt(p)) r *= geo_ld(g, p, G_RSPHEREMP);
+      if (is_interior_pt(p)) {
+        r *= geo_ld(g, p, G_RSPHEREMP);
+        if (TAVG) r = (qa[p == 5 ? 0 : p == 6 ? 1 : p == 9 ? 2 : 3] + 2.0 * r) / 3.0;
+      }
       out[p * NLEV] = r;
     }
   }
@@ -333,14 +329,14 @@ static int tracer_chunk() {
   return qc;
 }
 
-void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int dss_opt) {
+void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int dss_opt, int tavg_n0_qdp) {
   const int nq = S.p.qsize;
   if (!S.nelemd || !nq) return;
   const int mode = rhs_multiplier == 0.0 ? 0 : rhs_multiplier == 1.0 ? 1 : 2;
   if (mode == 2) S.rhs_viss = 3.0;  // compute_biharmonic_pre :196-214
   EulerArgs a{S.geo, S.tensorvisc, S.qdp, S.qtens_biharmonic, S.qlim, S.derived_dp, S.divdp_proj, S.divdp,
               S.derived_vn0, S.dpdiss_ave, S.dpdiss_biharmonic, dss_var(dss_opt), S.nelemd, nq, tracer_chunk(),
-              n0_qdp, np1_qdp, dt, rhs_multiplier * dt, S.p.nu_p, S.p.nu_q, S.rhs_viss, mode, S.p.limiter_option,
+              n0_qdp, np1_qdp, dt, rhs_multiplier * dt, S.p.nu_p, S.p.nu_q, S.rhs_viss, mode, tavg_n0_qdp, S.p.limiter_option,
               S.p.consthv ? 1 : 0};
   const dim3 grid(nblocks_flat(S.nelemd), (nq + a.qchunk - 1) / a.qchunk);
   PROBE(K_EULER_QMINMAX);
@@ -363,9 +359,13 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   const size_t smem = (size_t)(hv ? advect_slots<true>() : advect_slots<false>()) * TPB * sizeof(double);
   static bool attr = false;
   if (!attr) {
-    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  advect_slots<true>() * TPB * (int)sizeof(double)));
-    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 advect_slots<true>() * TPB * (int)sizeof(double)));
+    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 advect_slots<false>() * TPB * (int)sizeof(double)));
+    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  advect_slots<false>() * TPB * (int)sizeof(double)));
     attr = true;
   }
@@ -375,15 +375,18 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   const bool separate = (fdss == S.divdp_proj && a.rhsmdt != 0.0);
   if (separate) a.f_dss = nullptr;
   PROBE(K_EULER_ADVECT);
-  if (hv) euler_advect_kernel<true><<<grid, TPB, smem, S.stream>>>(a);
-  else euler_advect_kernel<false><<<grid, TPB, smem, S.stream>>>(a);
+  const bool tavg = tavg_n0_qdp >= 0;
+  if (hv && tavg) euler_advect_kernel<true, true><<<grid, TPB, smem, S.stream>>>(a);
+  else if (hv) euler_advect_kernel<true, false><<<grid, TPB, smem, S.stream>>>(a);
+  else if (tavg) euler_advect_kernel<false, true><<<grid, TPB, smem, S.stream>>>(a);
+  else euler_advect_kernel<false, false><<<grid, TPB, smem, S.stream>>>(a);
   KERNEL_LAUNCHED(K_EULER_ADVECT);
   if (separate) {
     PROBE(K_EULER_FDSS);
     euler_fdss_kernel<<<S.nelemd, 288, 0, S.stream>>>(fdss, S.geo);
     KERNEL_LAUNCHED(K_EULER_FDSS);
   }
-  dss_exchange(fields_euler(np1_qdp, dss_opt), true);  // exchange_qdp_dss_var :509-512
+  dss_exchange(fields_euler(np1_qdp, dss_opt, tavg_n0_qdp), true);  // exchange_qdp_dss_var :509-512
 }
 
 void euler_qdp_time_avg(int n0_qdp, int np1_qdp) {

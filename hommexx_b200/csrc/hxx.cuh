@@ -93,6 +93,10 @@ static_assert(sizeof(DssNode) == 32, "DssNode layout");
 constexpr int MAX_DSS_FIELDS = QSIZE_D + 1;
 struct FieldList {
   int nf;
+  // qdp_time_avg fused into the exchange: after the DSS, the first navg fields become
+  // (partner + 2 * field) / 3 with partner = the same point avg_delta doubles away
+  int navg = 0;
+  long long avg_delta = 0;
   double* base[MAX_DSS_FIELDS];       // element 0 of each field
   long long estride[MAX_DSS_FIELDS];  // doubles between consecutive elements
 };
@@ -141,8 +145,10 @@ struct Session {
   double *vstar = nullptr, *dpdissk = nullptr, *dp_star = nullptr;  // test-visible scratch
   double *qdp = nullptr, *qtens_biharmonic = nullptr, *qlim = nullptr, *qlim_x = nullptr, *Q = nullptr;
   // exchange plan
-  DssNode* nodes = nullptr;
+  DssNode* nodes = nullptr;  // generic remainder (cube vertices, nodes with off-rank sharers)
   int nnodes = 0;
+  void *dss_pairs = nullptr, *dss_quads = nullptr;  // lean lists (dss.cu: DssPair / DssQuad)
+  int npairs = 0, nquads = 0;
   int* nbr8 = nullptr;  // [nelemd][8] neighbour lid (>=0), ~halo_conn (<0) or DSS_NONE
   // halo (multi-GPU)
   int n_halo_pts = 0;           // receive points (edge = 4, corner = 1 per remote connection)
@@ -199,6 +205,35 @@ inline int nblocks_elem(int nelem) { return (nelem + EPB - 1) / EPB; }
 constexpr int TPB = 128;
 inline int nblocks_flat(int nelem) { return (int)(((long long)nelem * NLEV + TPB - 1) / TPB); }
 
+// ---- device helpers shared by the kernels ---------------------------------------------------
+#ifdef __CUDACC__
+// cp.async staging (LDGSTS): a thread streams 8-byte words into its own shared-memory slots
+// ahead of the arithmetic, so HBM latency hides behind FP64 work without holding the in-flight
+// data in registers.
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// x / d given r = 1.0 / d (correctly rounded): q = RN(x r) is within one ulp of x/d, the FMA
+// residual e = x - d q is exact, and RN(q + e r) is then the correctly rounded quotient
+// (Markstein). Exactness needs the residual to stay normal, so operands outside a wide safe
+// exponent window (and zeros, infinities, NaNs) take the IEEE division instead. d must be a
+// normal number of moderate magnitude (layer thicknesses, small constants).
+__device__ __forceinline__ double div_rcp(double x, double d, double r) {
+  const unsigned ex = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
+  if (ex - 423u > 1200u) return x / d;
+  const double q = x * r;
+  const double e = fma(-d, q, x);
+  return fma(e, r, q);
+}
+#endif
+
 // ---- phases (each defined in its own .cu) -------------------------------------------------
 // dss.cu
 void build_exchange_plan();
@@ -208,7 +243,7 @@ void scale_interior_rspheremp(const FieldList& fl);      // the 4 interior point
 void minmax_exchange();                                  // qlim -> qlim (neighbourhood min/max)
 FieldList fields_caar(int tl);
 FieldList fields_hv();
-FieldList fields_euler(int tq, int dss_opt);
+FieldList fields_euler(int tq, int dss_opt, int tavg_n0_qdp = -1);
 FieldList fields_qtens();
 double* dss_var(int dss_opt);
 // caar.cu
@@ -221,7 +256,9 @@ void update_q(int np1_qdp, int np1);
 void hypervis_run(int np1, double dt, double eta_ave_w);
 // euler.cu
 void euler_precompute_divdp();
-void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int dss_opt);
+// tavg_n0_qdp >= 0 fuses qdp_time_avg(tavg_n0_qdp, np1_qdp) into this stage (its advection
+// kernel does the interior points, its DSS the boundary nodes)
+void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int dss_opt, int tavg_n0_qdp = -1);
 void euler_qdp_time_avg(int n0_qdp, int np1_qdp);
 // remap.cu
 void vertical_remap(int np1, int np1_qdp);

@@ -180,8 +180,8 @@ static void prim_advec_tracers_remap_RK2(double dt) {
   euler_precompute_divdp();
   euler_step(S.np1_qdp, S.n0_qdp, dt / 2.0, 0.0, DSS_DIV_VDP_AVE);
   euler_step(S.np1_qdp, S.np1_qdp, dt / 2.0, 1.0, DSS_ETA);
-  euler_step(S.np1_qdp, S.np1_qdp, dt / 2.0, 2.0, DSS_OMEGA);
-  euler_qdp_time_avg(S.n0_qdp, S.np1_qdp);
+  // the last stage also applies qdp_time_avg(n0_qdp, np1_qdp) (:88), fused into its stores
+  euler_step(S.np1_qdp, S.np1_qdp, dt / 2.0, 2.0, DSS_OMEGA, S.n0_qdp);
 }
 
 // prim_step.cpp:20-103
@@ -560,8 +560,9 @@ void prim_run_subcycle_c(const double* dt, int* nstep, int* nm1, int* n0, int* n
     prim_step(*dt);
   }
   update_tracers_levels();
-  vertical_remap(S.np1, S.np1_qdp);  // :131
-  update_q(S.np1_qdp, S.np1);        // :138
+  // :131 and :138 — the remap kernel also stores Q = Qdp / dp for every tracer (update_q fused
+  // into its tracer store); without tracers there is nothing to update
+  vertical_remap(S.np1, S.np1_qdp);
   check_remap_flag();                // RemapFunctor.hpp:190-198 (one host sync per call)
   update_dynamics_levels();
   *nstep = S.nstep; *nm1 = S.nm1; *n0 = S.n0; *np1 = S.np1;

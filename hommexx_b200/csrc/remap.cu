@@ -1,54 +1,81 @@
 // Vertical remap (rsplit > 0) — replaces RemapFunctor.hpp, PpmRemap.hpp and
 // VerticalRemapManager of the reference: Lagrangian levels -> reference levels with PPM
-// (mirrored boundaries, optional fixed-parabola variant) for u*dp, v*dp, T*dp and every Qdp.
+// (mirrored boundaries, optional fixed-parabola variant) for u*dp, v*dp, T*dp and every Qdp,
+// with update_q (prim_driver.cpp:171-206, Q = Qdp / dp) fused into the tracer store.
 //
-// One warp per column, lanes = levels (coalesced 576-byte column loads/stores). The column's
-// grid data (partitions, kid, z2, ppmdx) are built once in shared memory and reused by all
-// 3+qsize fields. The three prefix sums (source/target interfaces, tracer mass) run in the
-// reference's sequential order on one lane, so results are bit-identical to the reference's
-// serial path (PpmRemap.hpp:226-247,524-566).
+// Mapping. A block owns RC = 4 columns (one GLL row of an element) and all 3 + qsize fields.
+// Phase 1: one warp per column builds the column's grid data in shared memory (source/target
+// partitions, kid, the integration bounds, the ten ppmdx coefficient rows) — shared by every
+// field. Phase 2: ONE THREAD PER (column, field) sweeps the column top-down once, holding the
+// PPM stencil (cell means, limited slopes, interface values) in a register window; the
+// remapped masses are produced by a merge of the source and target grids (kid is monotone), so
+// no per-field array ever exists in shared memory. Lanes of a warp share the column, so the
+// coefficient reads are shared-memory broadcasts and the merge is branch-uniform. Field data
+// moves through per-warp staging rows: cp.async brings CH levels of 32 fields at a time
+// (32-byte segments, two chunks ahead of the arithmetic) and results leave the same way, so
+// global accesses stay sector-coalesced although each thread walks its own column.
+// The prefix sums (source/target interfaces, mass above a cell) run in the reference's
+// sequential order, and divisions by a value that is reused across fields use its correctly
+// rounded reciprocal plus one FMA correction (bit-identical to IEEE division, see div_rcp), so
+// results stay bit-identical to the reference's serial path (PpmRemap.hpp:226-247,524-566).
 // Algorithmic HBM traffic per column: read+write of every remapped field (2 tiles per field per
-// element) plus one read of dp3d.
+// element), one read of dp3d and one write of Q per tracer.
 #include "hxx.cuh"
 
 HXX_DEFINE_CONSTANTS()
 
 namespace hxx {
 
-constexpr int RW = 6;  // warps (columns) per block
 constexpr int PAD = 2;
-constexpr int L2_ = NLEV + 2;
+constexpr int RC = 4;        // columns per block
+constexpr int CH = 4;        // levels per staged chunk (32 B per column-field)
+constexpr int RS = CH + 1;   // staging row stride in doubles (odd: conflict-free)
+constexpr int NBUF = 3;      // input chunks in flight per warp
+constexpr int NCHUNK = (NLEV + CH - 1) / CH;
 
-struct ColSmem {
-  double dpo[NLEV + 4], pio[NLEV + 2], pin[NLEV + 1], z2[NLEV], tgt[NLEV];
-  double ppmdx[10][NLEV + 2];
-  double ao[NLEV + 4], mass_o[NLEV + 2], dma[NLEV + 2], ai[NLEV + 1], coef[3][NLEV], massn[NLEV], var[NLEV];
+struct ColData {
+  double p0[NLEV + 2], p1[NLEV + 2], p2[NLEV + 2];                               // ppmdx 0..2, j = 0..NLEV+1
+  double p3[NLEV + 1], p4[NLEV + 1], p567[NLEV + 1], p8[NLEV + 1], p9[NLEV + 1];  // ppmdx 3..9, j = 0..NLEV
+  double dpo[NLEV + 4], rdpo[NLEV];
+  double tgt[NLEV], rtgt[NLEV];
+  double d1[NLEV], d2[NLEV], d3[NLEV];  // x2-x1, x2^2-x1^2, x2^3-x1^3 of integrate_parabola, x1 = -1/2, x2 = z2
+  double pio[NLEV + 2], pin[NLEV + 1];
   int kid[NLEV];
+  int ok;
+  int pad_;
 };
 
-__device__ __forceinline__ double integrate_parabola(double sq, double lin, double cst, double x1, double x2) {
-  return (cst * (x2 - x1) + lin * (x2 * x2 - x1 * x1) / 2.0) + sq * (x2 * x2 * x2 - x1 * x1 * x1) / 3.0;  // :668-673
-}
-
-// compute_partitions :506-597 + compute_integral_bounds :600-666 + compute_grids :366-413.
-// On entry c.dpo[PAD..] holds the source thickness and c.tgt the target thickness.
+// compute_partitions :506-597 + compute_integral_bounds :600-666 + compute_grids :366-413, by one
+// warp. On entry c.dpo[PAD..] holds the source thickness and c.tgt the target thickness.
 // Returns false when the target grid is not monotone (kid would leave the column): the reference
 // has undefined behaviour there; here the index is clamped and the caller raises the abort flag.
-__device__ bool ppm_column_grids(ColSmem& c, int lane) {
+__device__ bool ppm_column_grids(ColData& c, int lane) {
   bool ok = true;
-  if (lane == 0) {
+  if (lane < 2) {
+    // the two interface prefix sums, sequential (k ascending) as the reference, one lane each;
+    // loads are batched eight at a time so only the add chain is serial
+    const double* src = lane == 0 ? c.dpo + PAD : c.tgt;
+    double* dst = lane == 0 ? c.pio : c.pin;
     double acc = 0.0;
-    for (int k = 0; k < NLEV; ++k) { c.pio[k] = acc; acc += c.dpo[k + PAD]; }
-    c.pio[NLEV] = c.pio[NLEV - 1] + c.dpo[NLEV - 1 + PAD];
-    acc = 0.0;
-    for (int k = 0; k < NLEV; ++k) { c.pin[k] = acc; acc += c.tgt[k]; }
-    c.pio[NLEV + 1] = c.pio[NLEV] + 1.0;
-    c.pin[NLEV] = c.pio[NLEV];
-    for (int k = 0; k < 2; ++k) {
-      c.dpo[PAD - 1 - k] = c.dpo[k + PAD];
-      c.dpo[NLEV + PAD + k] = c.dpo[NLEV + PAD - 1 - k];
+    for (int k0 = 0; k0 < NLEV; k0 += 8) {
+      double v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (k0 + i < NLEV) ? src[k0 + i] : 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (k0 + i < NLEV) { dst[k0 + i] = acc; acc += v[i]; }
+    }
+    if (lane == 0) {
+      c.pio[NLEV] = c.pio[NLEV - 1] + c.dpo[NLEV - 1 + PAD];
+      c.pio[NLEV + 1] = c.pio[NLEV] + 1.0;
+      for (int k = 0; k < 2; ++k) {
+        c.dpo[PAD - 1 - k] = c.dpo[k + PAD];
+        c.dpo[NLEV + PAD + k] = c.dpo[NLEV + PAD - 1 - k];
+      }
     }
   }
+  __syncwarp();
+  if (lane == 0) c.pin[NLEV] = c.pio[NLEV];
   __syncwarp();
   for (int k = lane; k < NLEV; k += 32) {
     int kk = k + 1;
@@ -57,158 +84,286 @@ __device__ bool ppm_column_grids(ColSmem& c, int lane) {
     if (kk == NLEV + 1) kk = NLEV;
     if (kk < 1) { kk = 1; ok = false; }
     c.kid[k] = kk - 1;
-    c.z2[k] = (c.pin[k + 1] - (c.pio[kk - 1] + c.pio[kk]) * 0.5) / c.dpo[kk + 1 + PAD - 2];
+    const double z2 = (c.pin[k + 1] - (c.pio[kk - 1] + c.pio[kk]) * 0.5) / c.dpo[kk + 1 + PAD - 2];
+    // integrate_parabola :668-673 with x1 = -0.5: x1*x1 = 0.25 and x1*x1*x1 = -0.125 exactly
+    c.d1[k] = z2 - (-0.5);
+    c.d2[k] = z2 * z2 - 0.25;
+    c.d3[k] = z2 * z2 * z2 - (-0.125);
+    c.rdpo[k] = 1.0 / c.dpo[k + PAD];
+    c.rtgt[k] = 1.0 / c.tgt[k];
   }
   const double* dx = c.dpo;
   for (int j = lane; j < NLEV + 2; j += 32) {
-    c.ppmdx[0][j] = dx[j + 1] / (dx[j] + dx[j + 1] + dx[j + 2]);
-    c.ppmdx[1][j] = (2.0 * dx[j] + dx[j + 1]) / (dx[j + 1] + dx[j + 2]);
-    c.ppmdx[2][j] = (dx[j + 1] + 2.0 * dx[j + 2]) / (dx[j] + dx[j + 1]);
+    c.p0[j] = dx[j + 1] / (dx[j] + dx[j + 1] + dx[j + 2]);
+    c.p1[j] = (2.0 * dx[j] + dx[j + 1]) / (dx[j + 1] + dx[j + 2]);
+    c.p2[j] = (dx[j + 1] + 2.0 * dx[j + 2]) / (dx[j] + dx[j + 1]);
   }
   for (int j = lane; j < NLEV + 1; j += 32) {
-    c.ppmdx[3][j] = dx[j + 1] / (dx[j + 1] + dx[j + 2]);
-    c.ppmdx[4][j] = 1.0 / (dx[j] + dx[j + 1] + dx[j + 2] + dx[j + 3]);
-    c.ppmdx[5][j] = (2.0 * dx[j + 1] * dx[j + 2]) / (dx[j + 1] + dx[j + 2]);
-    c.ppmdx[6][j] = (dx[j] + dx[j + 1]) / (2.0 * dx[j + 1] + dx[j + 2]);
-    c.ppmdx[7][j] = (dx[j + 3] + dx[j + 2]) / (2.0 * dx[j + 2] + dx[j + 1]);
-    c.ppmdx[8][j] = dx[j + 1] * (dx[j] + dx[j + 1]) / (2.0 * dx[j + 1] + dx[j + 2]);
-    c.ppmdx[9][j] = dx[j + 2] * (dx[j + 2] + dx[j + 3]) / (dx[j + 1] + 2.0 * dx[j + 2]);
+    c.p3[j] = dx[j + 1] / (dx[j + 1] + dx[j + 2]);
+    c.p4[j] = 1.0 / (dx[j] + dx[j + 1] + dx[j + 2] + dx[j + 3]);
+    const double p5 = (2.0 * dx[j + 1] * dx[j + 2]) / (dx[j + 1] + dx[j + 2]);
+    const double p6 = (dx[j] + dx[j + 1]) / (2.0 * dx[j + 1] + dx[j + 2]);
+    const double p7 = (dx[j + 3] + dx[j + 2]) / (2.0 * dx[j + 2] + dx[j + 1]);
+    c.p567[j] = p5 * (p6 - p7);  // the leading factor of the (a0 - a1) term in compute_ppm
+    c.p8[j] = dx[j + 1] * (dx[j] + dx[j + 1]) / (2.0 * dx[j + 1] + dx[j + 2]);
+    c.p9[j] = dx[j + 2] * (dx[j + 2] + dx[j + 3]) / (dx[j + 1] + 2.0 * dx[j + 2]);
   }
   __syncwarp();
   return !__any_sync(0xffffffffu, !ok);
 }
 
-// compute_remap_phase :203-266 for one field of the column; c.var holds the field (mass units)
-// on entry and the remapped field on exit.
-__device__ void ppm_column_remap(ColSmem& c, int alg, int lane) {
-  for (int k = lane; k < NLEV; k += 32) c.ao[k + PAD] = c.var[k] / c.dpo[k + PAD];
-  __syncwarp();
-  if (lane == 0) {
-    for (int k0 = 0; k0 < 2; ++k0) {  // fill_cell_means_gs, mirrored :87-101
-      c.ao[PAD - 1 - k0] = c.ao[k0 + PAD];
-      c.ao[NLEV + PAD + k0] = c.ao[NLEV + PAD - 1 - k0];
+// limited slope of compute_ppm :416-447 (a0, a1, a2 = cell means j, j-1, j-2)
+__device__ __forceinline__ double ppm_dma(double a0, double a1, double a2, double p0, double p1, double p2) {
+  double r = 0.0;
+  if ((a0 - a1) * (a1 - a2) > 0.0) {
+    const double da = p0 * (p1 * (a0 - a1) + p2 * (a1 - a2));
+    r = fmin(fmin(fabs(da), 2.0 * fabs(a1 - a2)), 2.0 * fabs(a0 - a1)) * copysign(1.0, da);
+  }
+  return r;
+}
+// interface value :449-466
+__device__ __forceinline__ double ppm_ai(double a0, double a1, double dma_j1, double dma_j, double p3, double p4,
+                                         double p567, double p8, double p9) {
+  return a1 + p3 * (a0 - a1) + p4 * (p567 * (a0 - a1) - p8 * dma_j1 + p9 * dma_j);
+}
+
+// One (column, field) sweep of compute_remap_phase :203-266, top-down, PPM stencil in registers.
+//   tick(ln)   called by every lane (active or not) before level ln (2 <= ln < NLEV) is read
+//   load(k)    raw field value at level k; multiplied by the source thickness when `state`
+//   emit(k, x) remapped mass of target level k, in increasing k
+template <class Tick, class Load, class Emit>
+__device__ __forceinline__ void ppm_sweep(const ColData& c, int alg, bool active, bool state, Tick tick, Load load,
+                                          Emit emit) {
+  double Am1 = 0, A0 = 0, A1 = 0, DM0 = 0, AI0 = 0, V0 = 0, V1 = 0, Mc = 0.0, massn_prev = 0.0;
+  int kt = 0;
+  tick(0);
+  if (active) {
+    V0 = load(0); V1 = load(1);
+    if (state) { V0 *= c.dpo[0 + PAD]; V1 *= c.dpo[1 + PAD]; }  // ComputeExtrinsicsTag :255-268
+    A0 = div_rcp(V0, c.dpo[0 + PAD], c.rdpo[0]);
+    A1 = div_rcp(V1, c.dpo[1 + PAD], c.rdpo[1]);
+    Am1 = A0;  // mirrored ghosts :87-101: A(-1) = A(0), A(-2) = A(1)
+    const double dm_m1 = ppm_dma(A0, Am1, A1, c.p0[0], c.p1[0], c.p2[0]);
+    DM0 = ppm_dma(A1, A0, Am1, c.p0[1], c.p1[1], c.p2[1]);
+    AI0 = ppm_ai(A0, Am1, DM0, dm_m1, c.p3[0], c.p4[0], c.p567[0], c.p8[0], c.p9[0]);
+  }
+  const double r3 = 1.0 / 3.0, r6 = 1.0 / 6.0;
+  for (int cc = 0; cc < NLEV; ++cc) {
+    const int ln = cc + 2;  // level entering the window
+    if (ln < NLEV) tick(ln);
+    if (active) {
+      double A2, V2 = 0.0;
+      if (ln < NLEV) {
+        V2 = load(ln);
+        if (state) V2 *= c.dpo[ln + PAD];
+        A2 = div_rcp(V2, c.dpo[ln + PAD], c.rdpo[ln]);
+      } else {
+        A2 = ln == NLEV ? A1 : Am1;  // A(NLEV) = A(NLEV-1), A(NLEV+1) = A(NLEV-2)
+      }
+      const double DM1 = ppm_dma(A2, A1, A0, c.p0[cc + 2], c.p1[cc + 2], c.p2[cc + 2]);
+      const double AI1 = ppm_ai(A1, A0, DM1, DM0, c.p3[cc + 1], c.p4[cc + 1], c.p567[cc + 1], c.p8[cc + 1], c.p9[cc + 1]);
+      // parabola of cell cc :468-503
+      const double am = A0;
+      double al = AI0, ar = AI1;
+      if ((ar - am) * (am - al) <= 0.) { al = am; ar = am; }
+      if ((ar - al) * (am - (al + ar) / 2.0) > div_rcp((ar - al) * (ar - al), 6.0, r6)) al = 3.0 * am - 2.0 * ar;
+      if ((ar - al) * (am - (al + ar) / 2.0) < -div_rcp((ar - al) * (ar - al), 6.0, r6)) ar = 3.0 * am - 2.0 * al;
+      double c0 = 1.5 * am - (al + ar) / 4.0, c1 = ar - al, c2 = 3.0 * (-2.0 * am + (al + ar));
+      if (alg == 2 && (cc < 2 || cc >= NLEV - 2)) {  // PpmFixedParabola::apply_ppm_boundary :110-133
+        c0 = am; c1 = 0.0; c2 = 0.0;
+      }
+      // compute_remap :283-324 for every target level whose lower interface lies in cell cc
+      const double dpo_c = c.dpo[cc + PAD];
+      while (kt < NLEV && c.kid[kt] == cc) {
+        const double integral = (c0 * c.d1[kt] + c1 * c.d2[kt] / 2.0) + div_rcp(c2 * c.d3[kt], 3.0, r3);
+        const double massn = Mc + integral * dpo_c;
+        const double out = kt > 0 ? massn - massn_prev : massn;
+        massn_prev = massn;
+        emit(kt, out);
+        ++kt;
+      }
+      Mc += V0;  // mass above the next cell (serial sum, k ascending :226-247)
+      Am1 = A0; A0 = A1; A1 = A2; DM0 = DM1; AI0 = AI1; V0 = V1; V1 = V2;
     }
-    double acc = 0.0;
-    c.mass_o[0] = 0.0;
-    for (int k = 0; k < NLEV; ++k) { c.mass_o[k + 1] = acc; acc += c.var[k]; }
-    c.mass_o[NLEV + 1] = c.mass_o[NLEV] + c.var[NLEV - 1];
   }
-  __syncwarp();
-  // compute_ppm :416-503
-  for (int j = lane; j < NLEV + 2; j += 32) {
-    const double a0 = c.ao[j + PAD], a1 = c.ao[j + PAD - 1], a2 = c.ao[j + PAD - 2];
-    double r = 0.0;
-    if ((a0 - a1) * (a1 - a2) > 0.0) {
-      const double da = c.ppmdx[0][j] * (c.ppmdx[1][j] * (a0 - a1) + c.ppmdx[2][j] * (a1 - a2));
-      r = fmin(fmin(fabs(da), 2.0 * fabs(a1 - a2)), 2.0 * fabs(a0 - a1)) * copysign(1.0, da);
-    }
-    c.dma[j] = r;
-  }
-  __syncwarp();
-  for (int j = lane; j < NLEV + 1; j += 32) {
-    const double a0 = c.ao[j + PAD], a1 = c.ao[j + PAD - 1];
-    c.ai[j] = a1 + c.ppmdx[3][j] * (a0 - a1) +
-              c.ppmdx[4][j] * (c.ppmdx[5][j] * (c.ppmdx[6][j] - c.ppmdx[7][j]) * (a0 - a1) -
-                               c.ppmdx[8][j] * c.dma[j + 1] + c.ppmdx[9][j] * c.dma[j]);
-  }
-  __syncwarp();
-  for (int jp = lane; jp < NLEV; jp += 32) {
-    const int j = jp + 1;
-    const double am = c.ao[j + PAD - 1];
-    double al = c.ai[j - 1], ar = c.ai[j];
-    if ((ar - am) * (am - al) <= 0.) { al = am; ar = am; }
-    if ((ar - al) * (am - (al + ar) / 2.0) > (ar - al) * (ar - al) / 6.0) al = 3.0 * am - 2.0 * ar;
-    if ((ar - al) * (am - (al + ar) / 2.0) < -(ar - al) * (ar - al) / 6.0) ar = 3.0 * am - 2.0 * al;
-    double c0 = 1.5 * am - (al + ar) / 4.0, c1 = ar - al, c2 = 3.0 * (-2.0 * am + (al + ar));
-    if (alg == 2 && (jp < 2 || jp >= NLEV - 2)) {  // PpmFixedParabola::apply_ppm_boundary :110-133
-      c0 = am; c1 = 0.0; c2 = 0.0;
-    }
-    c.coef[0][jp] = c0; c.coef[1][jp] = c1; c.coef[2][jp] = c2;
-  }
-  __syncwarp();
-  // compute_remap :283-324
-  for (int k = lane; k < NLEV; k += 32) {
-    const int kk = c.kid[k];
-    const double integral = integrate_parabola(c.coef[2][kk], c.coef[1][kk], c.coef[0][kk], -0.5, c.z2[k]);
-    c.massn[k] = c.mass_o[kk + 1] + integral * c.dpo[kk + PAD];
-  }
-  __syncwarp();
-  for (int k = lane; k < NLEV; k += 32) c.var[k] = k > 0 ? c.massn[k] - c.massn[k - 1] : c.massn[0];
-  __syncwarp();
 }
 
 struct RemapArgs {
-  double *v, *t, *dp3d, *ps_v, *qdp;
+  double *v, *t, *dp3d, *ps_v, *qdp, *Q;
   int nelem, np1, np1_qdp, qsize, alg;
   int* invalid;
 };
 
-__global__ void __launch_bounds__(RW * 32) remap_kernel(const RemapArgs a) {
-  extern __shared__ unsigned char smraw[];
+// thread -> (column, field) of a block: per column `full` warps of 32 fields, then the last
+// NF % 32 fields of 32/G columns packed G lanes each into shared warps
+struct RemapMap {
+  int nf, full, rem, G, S, nwarps;
+};
+__host__ __device__ inline RemapMap remap_map(int qsize) {
+  RemapMap m;
+  m.nf = 3 + qsize;
+  m.full = m.nf / 32;
+  m.rem = m.nf % 32;
+  m.G = 0; m.S = 0;
+  if (m.rem) {
+    int g = 32 / RC;  // at most RC columns share a warp
+    while (g < m.rem) g *= 2;
+    m.G = g;
+    m.S = 32 / g;
+  }
+  m.nwarps = RC * m.full + (m.rem ? RC / m.S : 0);
+  return m;
+}
+
+constexpr int REMAP_MAX_WARPS = RC * ((3 + QSIZE_D) / 32) + ((3 + QSIZE_D) % 32 ? RC : 0);
+__global__ void __launch_bounds__(REMAP_MAX_WARPS * 32) remap_kernel(const RemapArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  ColData* cols = reinterpret_cast<ColData*>(smraw);
+  double* stage_all = reinterpret_cast<double*>(smraw + RC * sizeof(ColData));
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long col = (long long)blockIdx.x * RW + w;
-  if (col >= (long long)a.nelem * NPSQ) return;
-  ColSmem& c = reinterpret_cast<ColSmem*>(smraw)[w];
-  const int ie = (int)(col / NPSQ), p = (int)(col % NPSQ);
-  const double* src = a.dp3d + off_s(ie, a.np1) + p * NLEV;
-  bool bad = false;
-  for (int k = lane; k < NLEV; k += 32) {
-    const double s = src[k];
-    c.dpo[k + PAD] = s;
-    bad |= (isnan(s) || s < 0.0);  // check_source_thickness :439-464
-  }
-  if (__any_sync(0xffffffffu, bad)) {
-    // RemapFunctor.hpp:190-198: the run aborts after the launch; the column is left untouched
-    if (lane == 0) atomicOr(a.invalid, 1);
-    return;
-  }
-  __syncwarp();
-  // compute_ps_v :367-385 (serial sum, k ascending)
-  double ps = 0.0;
-  if (lane == 0) {
-    for (int k = 0; k < NLEV; ++k) ps += c.dpo[k + PAD];
-    ps += dc.hyai0 * dc.ps0;
-    a.ps_v[((size_t)ie * NTL + a.np1) * NPSQ + p] = ps;
-  }
-  ps = __shfl_sync(0xffffffffu, ps, 0);
-  // compute_target_thickness :417-437
-  for (int k = lane; k < NLEV; k += 32) c.tgt[k] = dc.dai[k] * dc.ps0 + dc.dbi[k] * ps;
-  __syncwarp();
-  if (!ppm_column_grids(c, lane) && lane == 0) atomicOr(a.invalid, 1);
-  const int nf = 3 + a.qsize;
-  for (int f = 0; f < nf; ++f) {
-    double* fld = f == 0 ? a.v + off_v(ie, a.np1, 0) : f == 1 ? a.v + off_v(ie, a.np1, 1)
-                : f == 2 ? a.t + off_s(ie, a.np1) : a.qdp + off_q(ie, a.np1_qdp, f - 3);
-    fld += p * NLEV;
-    const bool state = f < 3;
+  const RemapMap m = remap_map(a.qsize);
+  const int ie = blockIdx.x / (NPSQ / RC), p_first = (blockIdx.x % (NPSQ / RC)) * RC;
+
+  // ---- phase 1: column grids, one warp per column ------------------------------------------
+  for (int cl = w; cl < RC; cl += m.nwarps) {
+    ColData& c = cols[cl];
+    const int p = p_first + cl;
+    const double* src = a.dp3d + off_s(ie, a.np1) + p * NLEV;
+    bool bad = false;
     for (int k = lane; k < NLEV; k += 32) {
-      double x = fld[k];
-      if (state) x *= c.dpo[k + PAD];  // ComputeExtrinsicsTag :255-268
-      c.var[k] = x;
+      const double s = src[k];
+      c.dpo[k + PAD] = s;
+      bad |= (isnan(s) || s < 0.0);  // check_source_thickness :439-464
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (bad) {
+      // RemapFunctor.hpp:190-198: the run aborts after the launch; the column is left untouched
+      if (lane == 0) { atomicOr(a.invalid, 1); c.ok = 0; }
+      continue;
     }
     __syncwarp();
-    ppm_column_remap(c, a.alg, lane);
-    for (int k = lane; k < NLEV; k += 32) {
-      double x = c.var[k];
-      if (state) x /= c.tgt[k];  // ComputeIntrinsicsTag :294-307
-      fld[k] = x;
+    // compute_ps_v :367-385 (serial sum, k ascending)
+    double ps = 0.0;
+    if (lane == 0) {
+      for (int k0 = 0; k0 < NLEV; k0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (k0 + i < NLEV) ? c.dpo[k0 + i + PAD] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (k0 + i < NLEV) ps += v[i];
+      }
+      ps += dc.hyai0 * dc.ps0;
+      a.ps_v[((size_t)ie * NTL + a.np1) * NPSQ + p] = ps;
+      c.ok = 1;
     }
+    ps = __shfl_sync(0xffffffffu, ps, 0);
+    // compute_target_thickness :417-437
+    for (int k = lane; k < NLEV; k += 32) c.tgt[k] = dc.dai[k] * dc.ps0 + dc.dbi[k] * ps;
     __syncwarp();
+    if (!ppm_column_grids(c, lane) && lane == 0) atomicOr(a.invalid, 1);
   }
+  __syncthreads();
+
+  // ---- phase 2: one thread per (column, field) -----------------------------------------------
+  int cl, f, gsize;
+  if (w < RC * m.full) { cl = w / m.full; f = (w % m.full) * 32 + lane; gsize = 32; }
+  else {
+    const int rw = w - RC * m.full;
+    cl = rw * m.S + lane / m.G;
+    f = m.full * 32 + lane % m.G;
+    gsize = m.G;
+    if (lane % m.G >= m.rem) f = m.nf;  // padding lane
+  }
+  const ColData& c = cols[cl];
+  const bool active = f < m.nf && c.ok;
+  const unsigned amask = __ballot_sync(0xffffffffu, active);
+  if (!amask) return;
+  const int gfirst = lane - lane % gsize;  // first lane of this lane's column group
+  // the active lanes of the group (they share the column, hence the merge progress) and this
+  // lane's rank among them; padding lanes never reach the flush
+  const unsigned gmask = (gsize == 32 ? 0xffffffffu : (((1u << gsize) - 1u) << gfirst)) & amask;
+  const int gact = __popc(gmask), grank = __popc(gmask & ((1u << lane) - 1u));
+  const int p = p_first + cl;
+  // field bases of this lane's column (row r of the warp belongs to lane r)
+  double* const vbase = a.v + off_v(ie, a.np1, 0) + p * NLEV;
+  double* const tbase = a.t + off_s(ie, a.np1) + p * NLEV;
+  double* const qbase = a.qdp + off_q(ie, a.np1_qdp, 0) + p * NLEV;
+  double* const Qbase = a.Q + ((size_t)ie * QSIZE_D * NPSQ + p) * NLEV;
+  auto field_ptr = [&](int ff) -> double* {
+    return ff < 2 ? vbase + (size_t)ff * NLF : ff == 2 ? tbase : qbase + (size_t)(ff - 3) * NLF;
+  };
+  const bool state = f < 3;
+  double* const stage = stage_all + (size_t)w * (NBUF + 1) * 32 * RS;
+  double* const obuf = stage + NBUF * 32 * RS;
+  // cooperative chunk load: element e = i*32 + lane of the [32 rows][CH levels] chunk
+  auto prefetch = [&](int chunk) {
+    if (chunk < NCHUNK) {
+      double* dstb = stage + (chunk % NBUF) * 32 * RS;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int e = i * 32 + lane, row = e / CH, lev = e % CH, level = chunk * CH + lev;
+        // the row's field pointer is computed by the row's own lane
+        const unsigned long long rp = __shfl_sync(0xffffffffu, (unsigned long long)field_ptr(f < m.nf ? f : 0), row);
+        if (((amask >> row) & 1u) && level < NLEV) cp_async8(dstb + row * RS + lev, (const double*)rp + level);
+      }
+    }
+    cp_async_commit();
+  };
+  prefetch(0);
+  prefetch(1);
+  // staged raw value of this lane's field at `level` (chunk must have landed)
+  auto staged = [&](int level) { return stage[((level / CH) % NBUF) * 32 * RS + lane * RS + level % CH]; };
+  auto chunk_ready = [&](int chunk) {  // before the first read of a chunk: it has landed, refill the ring
+    cp_async_wait<1>();
+    __syncwarp();
+    prefetch(chunk + 2);
+  };
+
+  ppm_sweep(
+      c, a.alg, active, state,
+      [&](int ln) {  // uniform per step: level ln enters the window
+        if (ln % CH == 0) chunk_ready(ln / CH);
+      },
+      staged,
+      [&](int k, double out) {
+        obuf[lane * RS + k % CH] = out;
+        if ((k + 1) % CH == 0 || k + 1 == NLEV) {
+          // flush the finished chunk of this column group: its gact lanes store gact rows x CH levels
+          const int chunk = k / CH;
+          __syncwarp(gmask);
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const int e = i * gact + grank, rowl = e / CH, lev = e % CH, level = chunk * CH + lev;
+            const int row = gfirst + rowl, ff = f - (lane - gfirst) + rowl;  // fields are consecutive in a group
+            if (level < NLEV) {
+              const double val = obuf[row * RS + lev];
+              if (ff < 3) {
+                field_ptr(ff)[level] = div_rcp(val, c.tgt[level], c.rtgt[level]);  // ComputeIntrinsicsTag :294-307
+              } else {
+                field_ptr(ff)[level] = val;
+                Qbase[(size_t)(ff - 3) * NLF + level] = div_rcp(val, c.tgt[level], c.rtgt[level]);  // update_q
+              }
+            }
+          }
+          __syncwarp(gmask);
+        }
+      });
+  cp_async_wait<0>();
 }
 
 void vertical_remap(int np1, int np1_qdp) {
   if (!S.nelemd) return;
-  RemapArgs a{S.v, S.t, S.dp3d, S.ps_v, S.qdp, S.nelemd, np1, np1_qdp, S.p.qsize, S.p.remap_alg, S.invalid_flag};
-  constexpr size_t smem = RW * sizeof(ColSmem);
-  static bool attr = false;
-  if (!attr) {
+  RemapArgs a{S.v, S.t, S.dp3d, S.ps_v, S.qdp, S.Q, S.nelemd, np1, np1_qdp, S.p.qsize, S.p.remap_alg, S.invalid_flag};
+  const RemapMap m = remap_map(S.p.qsize);
+  const size_t smem = RC * sizeof(ColData) + (size_t)m.nwarps * (NBUF + 1) * 32 * RS * sizeof(double);
+  static size_t attr = 0;
+  if (smem > attr) {
     CUDA_OK(cudaFuncSetAttribute(remap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+    attr = smem;
   }
-  const long long ncol = (long long)S.nelemd * NPSQ;
   PROBE(K_REMAP);
-  remap_kernel<<<(unsigned)((ncol + RW - 1) / RW), RW * 32, smem, S.stream>>>(a);
+  remap_kernel<<<(unsigned)(S.nelemd * (NPSQ / RC)), m.nwarps * 32, smem, S.stream>>>(a);
   KERNEL_LAUNCHED(K_REMAP);
 }
 
@@ -220,27 +375,25 @@ void check_remap_flag() {
 }
 
 // ---- test hook: remap_Q_ppm semantics on caller-provided columns ---------------------------
-__global__ void __launch_bounds__(RW * 32)
+// One block per column: warp 0 builds the grids, then one thread per field sweeps the column
+// with the same ppm_sweep as the production kernel (plain loads/stores instead of the staging).
+__global__ void __launch_bounds__(64)
     remap_columns_kernel(int alg, int ncols, int nfields, const double* __restrict__ src_dp,
                          const double* __restrict__ tgt_dp, double* __restrict__ fields) {
-  extern __shared__ unsigned char smraw[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col = blockIdx.x * RW + w;
-  if (col >= ncols) return;
-  ColSmem& c = reinterpret_cast<ColSmem*>(smraw)[w];
-  for (int k = lane; k < NLEV; k += 32) {
-    c.dpo[k + PAD] = src_dp[(size_t)col * NLEV + k];
-    c.tgt[k] = tgt_dp[(size_t)col * NLEV + k];
+  __shared__ ColData c;
+  const int col = blockIdx.x, lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    for (int k = lane; k < NLEV; k += 32) {
+      c.dpo[k + PAD] = src_dp[(size_t)col * NLEV + k];
+      c.tgt[k] = tgt_dp[(size_t)col * NLEV + k];
+    }
+    __syncwarp();
+    ppm_column_grids(c, lane);
   }
-  __syncwarp();
-  ppm_column_grids(c, lane);
-  for (int f = 0; f < nfields; ++f) {
+  __syncthreads();
+  for (int f = threadIdx.x; f < nfields; f += blockDim.x) {
     double* fld = fields + ((size_t)f * ncols + col) * NLEV;
-    for (int k = lane; k < NLEV; k += 32) c.var[k] = fld[k];
-    __syncwarp();
-    ppm_column_remap(c, alg, lane);
-    for (int k = lane; k < NLEV; k += 32) fld[k] = c.var[k];
-    __syncwarp();
+    ppm_sweep(c, alg, true, false, [](int) {}, [&](int k) { return fld[k]; }, [&](int k, double x) { fld[k] = x; });
   }
 }
 
@@ -256,10 +409,8 @@ extern "C" void hxx_remap_columns(int alg, int ncols, int nfields, const double*
   CUDA_OK(cudaMemcpyAsync(d_src, src_dp, nc, cudaMemcpyHostToDevice, S.stream));
   CUDA_OK(cudaMemcpyAsync(d_tgt, tgt_dp, nc, cudaMemcpyHostToDevice, S.stream));
   CUDA_OK(cudaMemcpyAsync(d_f, fields, nfb, cudaMemcpyHostToDevice, S.stream));
-  constexpr size_t smem = RW * sizeof(ColSmem);
-  CUDA_OK(cudaFuncSetAttribute(remap_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PROBE(K_HOOK);
-  remap_columns_kernel<<<(ncols + RW - 1) / RW, RW * 32, smem, S.stream>>>(alg, ncols, nfields, d_src, d_tgt, d_f);
+  remap_columns_kernel<<<ncols, 64, 0, S.stream>>>(alg, ncols, nfields, d_src, d_tgt, d_f);
   KERNEL_LAUNCHED(K_HOOK);
   CUDA_OK(cudaMemcpyAsync(fields, d_f, nfb, cudaMemcpyDeviceToHost, S.stream));
   CUDA_OK(cudaStreamSynchronize(S.stream));
