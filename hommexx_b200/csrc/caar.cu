@@ -26,8 +26,18 @@ struct CaarArgs {
   int fold_rsp, store_phi;
 };
 
+#ifndef HXX_CAAR_E
+#define HXX_CAAR_E 2
+#endif
+#ifndef HXX_CAAR_MINB
+#define HXX_CAAR_MINB 2
+#endif
+// Elements per block: small blocks, several resident per SM, so that while one block walks its
+// columns serially (64 threads busy) the others keep the FP64 pipe and the memory system fed.
+constexpr int CAAR_E = HXX_CAAR_E;
+
 template <int E>
-__global__ void __launch_bounds__(E* NLEV, 1) caar_kernel(const CaarArgs a) {
+__global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const CaarArgs a) {
   constexpr int LS = NLEV + 1;  // odd column stride: conflict-free column walks
   extern __shared__ double sm[];
   double* s_p = sm;                  // dp -> pressure
@@ -68,20 +78,29 @@ __global__ void __launch_bounds__(E* NLEV, 1) caar_kernel(const CaarArgs a) {
   }
   __syncthreads();
   if (tid < E * NPSQ) {
-    // compute_pressure (:621-650) and the omega running sum (:854-889), two independent chains
+    // compute_pressure (:621-650) and the omega running sum (:854-889), two independent chains;
+    // loads are batched eight levels at a time so only the add chains are serial
     double* cp_ = s_p + tid * LS;
     double* cx = s_x + tid * LS;
     double dp_prev = 0.0, p_prev = dc.hyai0 * dc.ps0, integ = 0.0;
-#pragma unroll 8
-    for (int kk = 0; kk < NLEV; ++kk) {
-      const double d = cp_[kk];
-      const double pk = p_prev + 0.5 * (dp_prev + d);
-      cp_[kk] = pk;
-      p_prev = pk;
-      dp_prev = d;
-      const double dv = cx[kk];
-      cx[kk] = integ;
-      integ = integ + dv;
+    for (int k0 = 0; k0 < NLEV; k0 += 8) {
+      double d[8], dv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        d[i] = (k0 + i < NLEV) ? cp_[k0 + i] : 0.0;
+        dv[i] = (k0 + i < NLEV) ? cx[k0 + i] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (k0 + i < NLEV) {
+          const double pk = p_prev + 0.5 * (dp_prev + d[i]);
+          cp_[k0 + i] = pk;
+          p_prev = pk;
+          dp_prev = d[i];
+          cx[k0 + i] = integ;
+          integ = integ + dv[i];
+        }
+      }
     }
   }
   __syncthreads();
@@ -126,11 +145,17 @@ __global__ void __launch_bounds__(E* NLEV, 1) caar_kernel(const CaarArgs a) {
     const int iec = min(blockIdx.x * E + tid / NPSQ, a.nelem - 1);
     const double phis = a.geo[((size_t)iec * NPSQ + (tid % NPSQ)) * GEO_N + G_PHIS];
     double integ = 0.0;
-#pragma unroll 8
-    for (int kk = NLEV - 1; kk >= 0; --kk) {
-      const double ak = cx[kk];
-      cx[kk] = phis + 2.0 * integ + ak;
-      integ = integ + ak;
+    for (int k0 = NLEV - 1; k0 >= 0; k0 -= 8) {
+      double ak[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ak[i] = (k0 - i >= 0) ? cx[k0 - i] : 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (k0 - i >= 0) {
+          cx[k0 - i] = phis + 2.0 * integ + ak[i];
+          integ = integ + ak[i];
+        }
+      }
     }
   }
   __syncthreads();
@@ -212,14 +237,14 @@ void caar_run(int nm1, int n0, int np1, double dt, double eta_ave_w, int n0_qdp,
   if (!S.nelemd) return;
   CaarArgs a{S.geo, S.v, S.t, S.dp3d, S.derived_vn0, S.omega_p, S.phi, S.qdp, S.nelemd, nm1, n0, np1, n0_qdp,
              dt, eta_ave_w, with_dss ? 1 : 0, S.store_phi ? 1 : 0};
-  constexpr size_t smem = 2 * (size_t)EPB * NPSQ * (NLEV + 1) * sizeof(double);
+  constexpr size_t smem = 2 * (size_t)CAAR_E * NPSQ * (NLEV + 1) * sizeof(double);
   static bool attr = false;
   if (!attr) {
-    CUDA_OK(cudaFuncSetAttribute(caar_kernel<EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(caar_kernel<CAAR_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   PROBE(K_CAAR);
-  caar_kernel<EPB><<<nblocks_elem(S.nelemd), EPB * NLEV, smem, S.stream>>>(a);
+  caar_kernel<CAAR_E><<<(S.nelemd + CAAR_E - 1) / CAAR_E, CAAR_E * NLEV, smem, S.stream>>>(a);
   KERNEL_LAUNCHED(K_CAAR);
   if (with_dss) dss_exchange(fields_caar(np1), true);  // CaarFunctor.cpp:113
 }

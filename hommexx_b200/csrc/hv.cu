@@ -47,10 +47,8 @@ __global__ void __launch_bounds__(TPB, 2) hv_first_laplace_kernel(const HvArgs a
   for (int p = 0; p < NPSQ; ++p)
     if (is_interior_pt(p)) lap[p] *= geo_ld(g, p, G_RSPHEREMP);
   plane_store(a.dptens + off_f(ie) + k, lap);
-  double v1[NPSQ], l1[NPSQ];
-  plane_load(a.v + off_v(ie, a.np1, 0) + k, s);
-  plane_load(a.v + off_v(ie, a.np1, 1) + k, v1);
-  vlaplace_sphere_wk_contra(g, mi, a.nu_ratio1, s, v1, lap, l1);
+  double l1[NPSQ];
+  vlaplace_sphere_wk_contra_mem(g, mi, a.nu_ratio1, a.v + off_v(ie, a.np1, 0) + k, a.v + off_v(ie, a.np1, 1) + k, lap, l1);
   HXX_UNROLL
   for (int p = 0; p < NPSQ; ++p)
     if (is_interior_pt(p)) {
@@ -62,29 +60,46 @@ __global__ void __launch_bounds__(TPB, 2) hv_first_laplace_kernel(const HvArgs a
   plane_store(a.vtens + ((size_t)ie * 2 + 1) * NLF + k, l1);
 }
 
-// second Laplacian + TagHyperPreExchange
-__global__ void __launch_bounds__(TPB, 2) hv_second_laplace_pre_exchange_kernel(const HvArgs a) {
+// second Laplacian + TagHyperPreExchange. Two decisions keep the register footprint (and with
+// it the occupancy) in check: the scalar fields (T, dp3d) and the vector field are separate
+// kernels, and the nu_top sponge layer — extra Laplacians of the state on levels 0..2 only
+// (NUM_BIHARMONIC_LEV) — is a template flag: the SPONGE=true instantiation runs over just those
+// three levels of every element, the SPONGE=false one over the remaining levels, so 69 of 72
+// levels run code that never allocates registers for the sponge terms.
+template <bool SPONGE>
+__device__ __forceinline__ bool map_thread_hv2(int nelem, int nsponge, int& ie, int& k) {
+  const long long g = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (SPONGE) {
+    ie = (int)(g / nsponge);
+    k = (int)(g % nsponge);
+  } else {
+    const int nl = NLEV - nsponge;
+    ie = (int)(g / nl);
+    k = (int)(g % nl) + nsponge;
+  }
+  return ie < nelem;
+}
+
+template <bool SPONGE>
+__global__ void __launch_bounds__(TPB, SPONGE ? 2 : 3) hv_second_scalar_kernel(const HvArgs a, int nsponge) {
   int ie, k;
-  if (!map_thread(a.nelem, ie, k)) return;
+  if (!map_thread_hv2<SPONGE>(a.nelem, nsponge, ie, k)) return;
   const double* __restrict__ g = a.geo + (size_t)ie * NPSQ * GEO_N;
-  const double* __restrict__ mi = a.metinv + (size_t)ie * 4 * NPSQ;
   const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
-  const double* __restrict__ vs = a.consthv ? nullptr : a.vec_sph2cart + (size_t)ie * 6 * NPSQ;
   const double nst = (k == 0 ? 4.0 : k == 1 ? 2.0 : 1.0) * a.nu_top;  // HyperviscosityFunctorImpl.cpp:24-38
-  const bool sponge = a.nu_top > 0 && k < 3;                           // NUM_BIHARMONIC_LEV
   double s[NPSQ], lap[NPSQ], top[NPSQ];
   {  // T
     double* tt = a.ttens + off_f(ie) + k;
     plane_load(tt, s);
     if (a.consthv) laplace_simple(g, s, lap); else laplace_tensor(g, tv, s, lap);
-    if (sponge) {
+    if (SPONGE) {
       plane_load(a.t + off_s(ie, a.np1) + k, s);
       laplace_simple(g, s, top);
     }
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {
       lap[p] *= -a.nu_s;
-      if (sponge) lap[p] += nst * top[p];
+      if (SPONGE) lap[p] += nst * top[p];
     }
     plane_store(tt, lap);
   }
@@ -101,41 +116,53 @@ __global__ void __launch_bounds__(TPB, 2) hv_second_laplace_pre_exchange_kernel(
       dave[p * NLEV] += a.eta_ave_w * dp[p] / a.hypervis_subcycle;
       dbih[p * NLEV] += a.eta_ave_w * lap[p] / a.hypervis_subcycle;
     }
-    if (sponge) laplace_simple(g, dp, top);
+    if (SPONGE) laplace_simple(g, dp, top);
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {
       lap[p] *= -a.nu_p;
-      if (sponge) lap[p] += nst * top[p];
+      if (SPONGE) lap[p] += nst * top[p];
       lap[p] *= a.dt;
       lap[p] += dp[p] * geo_ld(g, p, G_SPHEREMP);
     }
     plane_store(dt_, lap);
   }
-  {  // v
-    double* vt0 = a.vtens + ((size_t)ie * 2 + 0) * NLF + k;
-    double* vt1 = a.vtens + ((size_t)ie * 2 + 1) * NLF + k;
-    double s1[NPSQ], l1[NPSQ], top1[NPSQ];
+}
+
+template <bool SPONGE>
+__global__ void __launch_bounds__(TPB, 2) hv_second_vector_kernel(const HvArgs a, int nsponge) {
+  int ie, k;
+  if (!map_thread_hv2<SPONGE>(a.nelem, nsponge, ie, k)) return;
+  const double* __restrict__ g = a.geo + (size_t)ie * NPSQ * GEO_N;
+  const double* __restrict__ mi = a.metinv + (size_t)ie * 4 * NPSQ;
+  const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
+  const double* __restrict__ vs = a.consthv ? nullptr : a.vec_sph2cart + (size_t)ie * 6 * NPSQ;
+  const double nst = (k == 0 ? 4.0 : k == 1 ? 2.0 : 1.0) * a.nu_top;
+  double* vt0 = a.vtens + ((size_t)ie * 2 + 0) * NLF + k;
+  double* vt1 = a.vtens + ((size_t)ie * 2 + 1) * NLF + k;
+  double lap[NPSQ], l1[NPSQ];
+  if (a.consthv) vlaplace_sphere_wk_contra_mem(g, mi, a.nu_ratio2, vt0, vt1, lap, l1);
+  else {
+    double s[NPSQ], s1[NPSQ];
     plane_load(vt0, s);
     plane_load(vt1, s1);
-    if (a.consthv) vlaplace_sphere_wk_contra(g, mi, a.nu_ratio2, s, s1, lap, l1);
-    else vlaplace_sphere_wk_cartesian(g, tv, vs, s, s1, lap, l1);
-    if (sponge) {
-      plane_load(a.v + off_v(ie, a.np1, 0) + k, s);
-      plane_load(a.v + off_v(ie, a.np1, 1) + k, s1);
-      vlaplace_sphere_wk_contra(g, mi, 1.0, s, s1, top, top1);
-    }
+    vlaplace_sphere_wk_cartesian(g, tv, vs, s, s1, lap, l1);
+  }
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) {
+    lap[p] *= -a.nu;
+    l1[p] *= -a.nu;
+  }
+  if (SPONGE) {
+    double top[NPSQ], top1[NPSQ];
+    vlaplace_sphere_wk_contra_mem(g, mi, 1.0, a.v + off_v(ie, a.np1, 0) + k, a.v + off_v(ie, a.np1, 1) + k, top, top1);
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {
-      lap[p] *= -a.nu;
-      l1[p] *= -a.nu;
-      if (sponge) {
-        lap[p] += nst * top[p];
-        l1[p] += nst * top1[p];
-      }
+      lap[p] += nst * top[p];
+      l1[p] += nst * top1[p];
     }
-    plane_store(vt0, lap);
-    plane_store(vt1, l1);
   }
+  plane_store(vt0, lap);
+  plane_store(vt1, l1);
 }
 
 // TagUpdateStates .hpp:134-158
@@ -176,9 +203,18 @@ void hypervis_run(int np1, double dt_in, double eta_ave_w) {
     hv_first_laplace_kernel<<<nb, TPB, 0, S.stream>>>(a);
     KERNEL_LAUNCHED(K_HV_FIRST);
     dss_exchange(fields_hv(), true);
-    PROBE(K_HV_SECOND);
-    hv_second_laplace_pre_exchange_kernel<<<nb, TPB, 0, S.stream>>>(a);
-    KERNEL_LAUNCHED(K_HV_SECOND);
+    {
+      const int nsp = p.nu_top > 0 ? (NLEV < 3 ? NLEV : 3) : 0;  // NUM_BIHARMONIC_LEV
+      const int nb_main = (int)(((long long)S.nelemd * (NLEV - nsp) + TPB - 1) / TPB);
+      const int nb_sp = (int)(((long long)S.nelemd * nsp + TPB - 1) / TPB);
+      PROBE(K_HV_SECOND);
+      if (nb_main) hv_second_scalar_kernel<false><<<nb_main, TPB, 0, S.stream>>>(a, nsp);
+      if (nb_main) hv_second_vector_kernel<false><<<nb_main, TPB, 0, S.stream>>>(a, nsp);
+      if (nb_sp) hv_second_scalar_kernel<true><<<nb_sp, TPB, 0, S.stream>>>(a, nsp);
+      if (nb_sp) hv_second_vector_kernel<true><<<nb_sp, TPB, 0, S.stream>>>(a, nsp);
+      KERNEL_LAUNCHED(K_HV_SECOND);
+      S.launches += 3;
+    }
     dss_exchange(fields_hv(), false);
     PROBE(K_HV_UPDATE);
     hv_update_states_kernel<<<S.nelemd, 288, 0, S.stream>>>(a);
