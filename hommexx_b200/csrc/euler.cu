@@ -62,10 +62,13 @@ __global__ void __launch_bounds__(TPB, 2)
 template <bool BIH>
 __global__ void __launch_bounds__(TPB, BIH ? 2 : 4) euler_qminmax_kernel(const EulerArgs a) {
   extern __shared__ double s_all[];
+  __shared__ double s_geo[BIH ? geo_span(TPB) * NPSQ * GEO_N : 1];
+  const int e_first = (int)(((long long)blockIdx.x * TPB) / NLEV);
+  if (BIH) stage_geo<geo_span(TPB), TPB>(s_geo, a.geo, e_first, a.nelem);
   int ie, k;
   if (!map_thread(a.nelem, ie, k)) return;
   double* const s_q = s_all + threadIdx.x;  // [2][16][TPB]
-  const double* __restrict__ g = a.geo + (size_t)ie * NPSQ * GEO_N;
+  const double* g = BIH ? s_geo + (ie - e_first) * NPSQ * GEO_N : a.geo;
   const int q0 = blockIdx.y * a.qchunk, q1 = min(a.qsize, q0 + a.qchunk);
   const double* const qin = a.qdp + off_q(ie, a.n0_qdp, 0) + k;
   auto prefetch = [&](int q, int buf) {
@@ -146,6 +149,9 @@ constexpr int advect_slots() { return 48 + NPSQ * ADV_NST * (HV ? 2 : 1); }
 template <bool HV, bool TAVG>
 __global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) euler_advect_kernel(const EulerArgs a) {
   extern __shared__ double s_all[];
+  __shared__ double s_geo[geo_span(TPB) * NPSQ * GEO_N];
+  const int e_first = (int)(((long long)blockIdx.x * TPB) / NLEV);
+  stage_geo<geo_span(TPB), TPB>(s_geo, a.geo, e_first, a.nelem);
   int ie, k;
   if (!map_thread(a.nelem, ie, k)) return;  // no block-wide barrier below: early exit is safe
   const int tid = threadIdx.x;
@@ -154,7 +160,7 @@ __global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eule
   double* const s_dpk = s_all + 32 * TPB + tid;
   double* const s_q = s_all + 48 * TPB + tid;
   double* const s_b = s_all + (48 + NPSQ * ADV_NST) * TPB + tid;
-  const double* __restrict__ g = a.geo + (size_t)ie * NPSQ * GEO_N;
+  const double* g = s_geo + (ie - e_first) * NPSQ * GEO_N;
   const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
   const int q0 = blockIdx.y * a.qchunk, q1 = min(a.qsize, q0 + a.qchunk);
   const double* const qin = a.qdp + off_q(ie, a.n0_qdp, 0) + k;

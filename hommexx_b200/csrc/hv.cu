@@ -66,6 +66,8 @@ __global__ void __launch_bounds__(TPB, 2) hv_first_laplace_kernel(const HvArgs a
 // (NUM_BIHARMONIC_LEV) — is a template flag: the SPONGE=true instantiation runs over just those
 // three levels of every element, the SPONGE=false one over the remaining levels, so 69 of 72
 // levels run code that never allocates registers for the sponge terms.
+constexpr int HV2_SPAN = (TPB + (NLEV > 3 ? NLEV - 3 : 1) - 2) / (NLEV > 3 ? NLEV - 3 : 1) + 1;
+
 template <bool SPONGE>
 __device__ __forceinline__ bool map_thread_hv2(int nelem, int nsponge, int& ie, int& k) {
   const long long g = (long long)blockIdx.x * TPB + threadIdx.x;
@@ -82,9 +84,14 @@ __device__ __forceinline__ bool map_thread_hv2(int nelem, int nsponge, int& ie, 
 
 template <bool SPONGE>
 __global__ void __launch_bounds__(TPB, SPONGE ? 2 : 3) hv_second_scalar_kernel(const HvArgs a, int nsponge) {
+  // the main (non-sponge) instantiation walks >= NLEV - 3 levels per element, so a block spans
+  // at most HV2_SPAN elements and reads their geometry from shared memory
+  __shared__ double s_geo[SPONGE ? 1 : HV2_SPAN * NPSQ * GEO_N];
+  const int e_first = SPONGE ? 0 : (int)(((long long)blockIdx.x * TPB) / (NLEV - nsponge));
+  if (!SPONGE) stage_geo<HV2_SPAN, TPB>(s_geo, a.geo, e_first, a.nelem);
   int ie, k;
   if (!map_thread_hv2<SPONGE>(a.nelem, nsponge, ie, k)) return;
-  const double* __restrict__ g = a.geo + (size_t)ie * NPSQ * GEO_N;
+  const double* g = SPONGE ? a.geo + (size_t)ie * NPSQ * GEO_N : s_geo + (ie - e_first) * NPSQ * GEO_N;
   const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
   const double nst = (k == 0 ? 4.0 : k == 1 ? 2.0 : 1.0) * a.nu_top;  // HyperviscosityFunctorImpl.cpp:24-38
   double s[NPSQ], lap[NPSQ], top[NPSQ];
@@ -130,9 +137,14 @@ __global__ void __launch_bounds__(TPB, SPONGE ? 2 : 3) hv_second_scalar_kernel(c
 
 template <bool SPONGE>
 __global__ void __launch_bounds__(TPB, 2) hv_second_vector_kernel(const HvArgs a, int nsponge) {
+  // the main (non-sponge) instantiation walks >= NLEV - 3 levels per element, so a block spans
+  // at most HV2_SPAN elements and reads their geometry from shared memory
+  __shared__ double s_geo[SPONGE ? 1 : HV2_SPAN * NPSQ * GEO_N];
+  const int e_first = SPONGE ? 0 : (int)(((long long)blockIdx.x * TPB) / (NLEV - nsponge));
+  if (!SPONGE) stage_geo<HV2_SPAN, TPB>(s_geo, a.geo, e_first, a.nelem);
   int ie, k;
   if (!map_thread_hv2<SPONGE>(a.nelem, nsponge, ie, k)) return;
-  const double* __restrict__ g = a.geo + (size_t)ie * NPSQ * GEO_N;
+  const double* g = SPONGE ? a.geo + (size_t)ie * NPSQ * GEO_N : s_geo + (ie - e_first) * NPSQ * GEO_N;
   const double* __restrict__ mi = a.metinv + (size_t)ie * 4 * NPSQ;
   const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
   const double* __restrict__ vs = a.consthv ? nullptr : a.vec_sph2cart + (size_t)ie * 6 * NPSQ;

@@ -227,8 +227,8 @@ __device__ __forceinline__ void cp_async_wait() {
 // normal number of moderate magnitude (layer thicknesses, small constants).
 __device__ __forceinline__ double div_rcp(double x, double d, double r) {
   const unsigned ex = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
-  if (ex - 423u > 1200u) return x / d;
   const double q = x * r;
+  if (ex - 423u > 1200u) return x == 0.0 ? q : x / d;  // x r is the correctly signed zero
   const double e = fma(-d, q, x);
   return fma(e, r, q);
 }

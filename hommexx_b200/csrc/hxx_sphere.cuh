@@ -9,9 +9,26 @@ namespace hxx {
 
 #define HXX_UNROLL _Pragma("unroll")
 
-__device__ __forceinline__ double geo_ld(const double* __restrict__ g, int p, int c) {
-  return __ldg(g + p * GEO_N + c);
+// g points at the element's geometry record, either in global memory or at the block's copy of
+// it in shared memory (stage_geo below); after inlining the compiler knows which and emits LDG
+// or a shared-memory broadcast load.
+__device__ __forceinline__ double geo_ld(const double* __restrict__ g, int p, int c) { return g[p * GEO_N + c]; }
+
+// Cooperative copy of the geometry records of the (at most NE) elements a block of the flat
+// (element, level) mapping touches. Every thread of the block must call it (it has a barrier).
+// Shared-memory reads do not queue behind the block's outstanding HBM requests in the L1
+// pipeline the way L1-hit global loads do, which matters because the operators re-read the
+// geometry for every tracer / field.
+template <int NE, int NT>
+__device__ __forceinline__ void stage_geo(double* s_geo, const double* __restrict__ geo, int e_first, int nelem) {
+  for (int i = threadIdx.x; i < NE * NPSQ * GEO_N; i += NT) {
+    const int e = e_first + i / (NPSQ * GEO_N);
+    if (e < nelem) s_geo[i] = __ldg(geo + (size_t)e_first * NPSQ * GEO_N + i);
+  }
+  __syncthreads();
 }
+// elements spanned by NT consecutive (element, level) threads
+__host__ __device__ constexpr int geo_span(int nt) { return (nt + NLEV - 2) / NLEV + 1; }
 
 // load / store one level of a field tile ([16][NLEV], the thread's level already added to ptr)
 __device__ __forceinline__ void plane_load(const double* __restrict__ f, double (&s)[NPSQ]) {

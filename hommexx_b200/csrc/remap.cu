@@ -30,8 +30,12 @@ constexpr int PAD = 2;
 constexpr int RC = 4;        // columns per block
 constexpr int CH = 4;        // levels per staged chunk (32 B per column-field)
 constexpr int RS = CH + 1;   // staging row stride in doubles (odd: conflict-free)
-constexpr int NBUF = 3;      // input chunks in flight per warp
+constexpr int NBUF = 2;      // input chunks in flight per warp
 constexpr int NCHUNK = (NLEV + CH - 1) / CH;
+// per-warp staging: NBUF input chunks, the output chunk and its Q twin ([32 rows][RS] each), and
+// the two per-row pointer tables (field, Q); the input rows double as phase-1 scratch
+constexpr int STAGE_PER_WARP = (NBUF + 2) * 32 * RS + 64;
+static_assert(STAGE_PER_WARP >= 2 * NLEV + 3, "phase-1 scratch does not fit the staging rows");
 
 struct ColData {
   double p0[NLEV + 2], p1[NLEV + 2], p2[NLEV + 2];                               // ppmdx 0..2, j = 0..NLEV+1
@@ -39,7 +43,6 @@ struct ColData {
   double dpo[NLEV + 4], rdpo[NLEV];
   double tgt[NLEV], rtgt[NLEV];
   double d1[NLEV], d2[NLEV], d3[NLEV];  // x2-x1, x2^2-x1^2, x2^3-x1^3 of integrate_parabola, x1 = -1/2, x2 = z2
-  double pio[NLEV + 2], pin[NLEV + 1];
   int kid[NLEV];
   int ok;
   int pad_;
@@ -49,13 +52,16 @@ struct ColData {
 // warp. On entry c.dpo[PAD..] holds the source thickness and c.tgt the target thickness.
 // Returns false when the target grid is not monotone (kid would leave the column): the reference
 // has undefined behaviour there; here the index is clamped and the caller raises the abort flag.
-__device__ bool ppm_column_grids(ColData& c, int lane) {
+// `scratch` holds the two interface arrays pio[NLEV+2], pin[NLEV+1] (only needed here).
+__device__ bool ppm_column_grids(ColData& c, double* scratch, int lane) {
   bool ok = true;
+  double* const pio = scratch;
+  double* const pin = scratch + NLEV + 2;
   if (lane < 2) {
     // the two interface prefix sums, sequential (k ascending) as the reference, one lane each;
     // loads are batched eight at a time so only the add chain is serial
     const double* src = lane == 0 ? c.dpo + PAD : c.tgt;
-    double* dst = lane == 0 ? c.pio : c.pin;
+    double* dst = lane == 0 ? pio : pin;
     double acc = 0.0;
     for (int k0 = 0; k0 < NLEV; k0 += 8) {
       double v[8];
@@ -66,8 +72,8 @@ __device__ bool ppm_column_grids(ColData& c, int lane) {
         if (k0 + i < NLEV) { dst[k0 + i] = acc; acc += v[i]; }
     }
     if (lane == 0) {
-      c.pio[NLEV] = c.pio[NLEV - 1] + c.dpo[NLEV - 1 + PAD];
-      c.pio[NLEV + 1] = c.pio[NLEV] + 1.0;
+      pio[NLEV] = pio[NLEV - 1] + c.dpo[NLEV - 1 + PAD];
+      pio[NLEV + 1] = pio[NLEV] + 1.0;
       for (int k = 0; k < 2; ++k) {
         c.dpo[PAD - 1 - k] = c.dpo[k + PAD];
         c.dpo[NLEV + PAD + k] = c.dpo[NLEV + PAD - 1 - k];
@@ -75,16 +81,16 @@ __device__ bool ppm_column_grids(ColData& c, int lane) {
     }
   }
   __syncwarp();
-  if (lane == 0) c.pin[NLEV] = c.pio[NLEV];
+  if (lane == 0) pin[NLEV] = pio[NLEV];
   __syncwarp();
   for (int k = lane; k < NLEV; k += 32) {
     int kk = k + 1;
-    while (kk <= NLEV + 1 && c.pio[kk - 1] <= c.pin[k + 1]) kk++;
+    while (kk <= NLEV + 1 && pio[kk - 1] <= pin[k + 1]) kk++;
     kk--;
     if (kk == NLEV + 1) kk = NLEV;
     if (kk < 1) { kk = 1; ok = false; }
     c.kid[k] = kk - 1;
-    const double z2 = (c.pin[k + 1] - (c.pio[kk - 1] + c.pio[kk]) * 0.5) / c.dpo[kk + 1 + PAD - 2];
+    const double z2 = (pin[k + 1] - (pio[kk - 1] + pio[kk]) * 0.5) / c.dpo[kk + 1 + PAD - 2];
     // integrate_parabola :668-673 with x1 = -0.5: x1*x1 = 0.25 and x1*x1*x1 = -0.125 exactly
     c.d1[k] = z2 - (-0.5);
     c.d2[k] = z2 * z2 - 0.25;
@@ -128,63 +134,68 @@ __device__ __forceinline__ double ppm_ai(double a0, double a1, double dma_j1, do
 }
 
 // One (column, field) sweep of compute_remap_phase :203-266, top-down, PPM stencil in registers.
-//   tick(ln)   called by every lane (active or not) before level ln (2 <= ln < NLEV) is read
-//   load(k)    raw field value at level k; multiplied by the source thickness when `state`
-//   emit(k, x) remapped mass of target level k, in increasing k
+//   tick(ln)      called by every lane (active or not) before level ln (2 <= ln < NLEV) is read
+//   load(k)       raw field value at level k; multiplied by the source thickness when `state`
+//   emit(k, x, t) remapped mass x of target level k (increasing k) and t = x / target thickness
 template <class Tick, class Load, class Emit>
 __device__ __forceinline__ void ppm_sweep(const ColData& c, int alg, bool active, bool state, Tick tick, Load load,
                                           Emit emit) {
   double Am1 = 0, A0 = 0, A1 = 0, DM0 = 0, AI0 = 0, V0 = 0, V1 = 0, Mc = 0.0, massn_prev = 0.0;
-  int kt = 0;
+  int kt = 0, kid_next = -1;
+  const double r3 = 1.0 / 3.0, r6 = 1.0 / 6.0;
+  // the step for source cell cc once A(cc+2) is known (V2 = its mass, unused past the column end)
+  auto body = [&](int cc, double A2, double V2) {
+    const double DM1 = ppm_dma(A2, A1, A0, c.p0[cc + 2], c.p1[cc + 2], c.p2[cc + 2]);
+    const double AI1 = ppm_ai(A1, A0, DM1, DM0, c.p3[cc + 1], c.p4[cc + 1], c.p567[cc + 1], c.p8[cc + 1], c.p9[cc + 1]);
+    // parabola of cell cc :468-503
+    const double am = A0;
+    double al = AI0, ar = AI1;
+    if ((ar - am) * (am - al) <= 0.) { al = am; ar = am; }
+    if ((ar - al) * (am - (al + ar) / 2.0) > div_rcp((ar - al) * (ar - al), 6.0, r6)) al = 3.0 * am - 2.0 * ar;
+    if ((ar - al) * (am - (al + ar) / 2.0) < -div_rcp((ar - al) * (ar - al), 6.0, r6)) ar = 3.0 * am - 2.0 * al;
+    double c0 = 1.5 * am - (al + ar) / 4.0, c1 = ar - al, c2 = 3.0 * (-2.0 * am + (al + ar));
+    if (alg == 2 && (cc < 2 || cc >= NLEV - 2)) {  // PpmFixedParabola::apply_ppm_boundary :110-133
+      c0 = am; c1 = 0.0; c2 = 0.0;
+    }
+    // compute_remap :283-324 for every target level whose lower interface lies in cell cc
+    const double dpo_c = c.dpo[cc + PAD];
+    while (kid_next == cc) {
+      const double integral = (c0 * c.d1[kt] + c1 * c.d2[kt] / 2.0) + div_rcp(c2 * c.d3[kt], 3.0, r3);
+      const double massn = Mc + integral * dpo_c;
+      const double out = kt > 0 ? massn - massn_prev : massn;
+      massn_prev = massn;
+      emit(kt, out, div_rcp(out, c.tgt[kt], c.rtgt[kt]));
+      ++kt;
+      kid_next = kt < NLEV ? c.kid[kt] : -1;
+    }
+    Mc += V0;  // mass above the next cell (serial sum, k ascending :226-247)
+    Am1 = A0; A0 = A1; A1 = A2; DM0 = DM1; AI0 = AI1; V0 = V1; V1 = V2;
+  };
   tick(0);
   if (active) {
-    V0 = load(0); V1 = load(1);
-    if (state) { V0 *= c.dpo[0 + PAD]; V1 *= c.dpo[1 + PAD]; }  // ComputeExtrinsicsTag :255-268
+    V0 = load(0) * (state ? c.dpo[0 + PAD] : 1.0);  // ComputeExtrinsicsTag :255-268
+    V1 = load(1) * (state ? c.dpo[1 + PAD] : 1.0);
     A0 = div_rcp(V0, c.dpo[0 + PAD], c.rdpo[0]);
     A1 = div_rcp(V1, c.dpo[1 + PAD], c.rdpo[1]);
     Am1 = A0;  // mirrored ghosts :87-101: A(-1) = A(0), A(-2) = A(1)
     const double dm_m1 = ppm_dma(A0, Am1, A1, c.p0[0], c.p1[0], c.p2[0]);
     DM0 = ppm_dma(A1, A0, Am1, c.p0[1], c.p1[1], c.p2[1]);
     AI0 = ppm_ai(A0, Am1, DM0, dm_m1, c.p3[0], c.p4[0], c.p567[0], c.p8[0], c.p9[0]);
+    kid_next = c.kid[0];
   }
-  const double r3 = 1.0 / 3.0, r6 = 1.0 / 6.0;
-  for (int cc = 0; cc < NLEV; ++cc) {
+#pragma unroll 2
+  for (int cc = 0; cc < NLEV - 2; ++cc) {
     const int ln = cc + 2;  // level entering the window
-    if (ln < NLEV) tick(ln);
+    tick(ln);
     if (active) {
-      double A2, V2 = 0.0;
-      if (ln < NLEV) {
-        V2 = load(ln);
-        if (state) V2 *= c.dpo[ln + PAD];
-        A2 = div_rcp(V2, c.dpo[ln + PAD], c.rdpo[ln]);
-      } else {
-        A2 = ln == NLEV ? A1 : Am1;  // A(NLEV) = A(NLEV-1), A(NLEV+1) = A(NLEV-2)
-      }
-      const double DM1 = ppm_dma(A2, A1, A0, c.p0[cc + 2], c.p1[cc + 2], c.p2[cc + 2]);
-      const double AI1 = ppm_ai(A1, A0, DM1, DM0, c.p3[cc + 1], c.p4[cc + 1], c.p567[cc + 1], c.p8[cc + 1], c.p9[cc + 1]);
-      // parabola of cell cc :468-503
-      const double am = A0;
-      double al = AI0, ar = AI1;
-      if ((ar - am) * (am - al) <= 0.) { al = am; ar = am; }
-      if ((ar - al) * (am - (al + ar) / 2.0) > div_rcp((ar - al) * (ar - al), 6.0, r6)) al = 3.0 * am - 2.0 * ar;
-      if ((ar - al) * (am - (al + ar) / 2.0) < -div_rcp((ar - al) * (ar - al), 6.0, r6)) ar = 3.0 * am - 2.0 * al;
-      double c0 = 1.5 * am - (al + ar) / 4.0, c1 = ar - al, c2 = 3.0 * (-2.0 * am + (al + ar));
-      if (alg == 2 && (cc < 2 || cc >= NLEV - 2)) {  // PpmFixedParabola::apply_ppm_boundary :110-133
-        c0 = am; c1 = 0.0; c2 = 0.0;
-      }
-      // compute_remap :283-324 for every target level whose lower interface lies in cell cc
-      const double dpo_c = c.dpo[cc + PAD];
-      while (kt < NLEV && c.kid[kt] == cc) {
-        const double integral = (c0 * c.d1[kt] + c1 * c.d2[kt] / 2.0) + div_rcp(c2 * c.d3[kt], 3.0, r3);
-        const double massn = Mc + integral * dpo_c;
-        const double out = kt > 0 ? massn - massn_prev : massn;
-        massn_prev = massn;
-        emit(kt, out);
-        ++kt;
-      }
-      Mc += V0;  // mass above the next cell (serial sum, k ascending :226-247)
-      Am1 = A0; A0 = A1; A1 = A2; DM0 = DM1; AI0 = AI1; V0 = V1; V1 = V2;
+      const double dl = c.dpo[ln + PAD];
+      const double V2 = load(ln) * (state ? dl : 1.0);
+      body(cc, div_rcp(V2, dl, c.rdpo[ln]), V2);
     }
+  }
+  if (active) {
+    body(NLEV - 2, A1, 0.0);   // A(NLEV) = A(NLEV-1)
+    body(NLEV - 1, Am1, 0.0);  // A(NLEV+1) = A(NLEV-2)
   }
 }
 
@@ -261,7 +272,7 @@ __global__ void __launch_bounds__(REMAP_MAX_WARPS * 32) remap_kernel(const Remap
     // compute_target_thickness :417-437
     for (int k = lane; k < NLEV; k += 32) c.tgt[k] = dc.dai[k] * dc.ps0 + dc.dbi[k] * ps;
     __syncwarp();
-    if (!ppm_column_grids(c, lane) && lane == 0) atomicOr(a.invalid, 1);
+    if (!ppm_column_grids(c, stage_all + (size_t)w * STAGE_PER_WARP, lane) && lane == 0) atomicOr(a.invalid, 1);
   }
   __syncthreads();
 
@@ -294,8 +305,15 @@ __global__ void __launch_bounds__(REMAP_MAX_WARPS * 32) remap_kernel(const Remap
     return ff < 2 ? vbase + (size_t)ff * NLF : ff == 2 ? tbase : qbase + (size_t)(ff - 3) * NLF;
   };
   const bool state = f < 3;
-  double* const stage = stage_all + (size_t)w * (NBUF + 1) * 32 * RS;
+  double* const stage = stage_all + (size_t)w * STAGE_PER_WARP;
   double* const obuf = stage + NBUF * 32 * RS;
+  double* const qbuf = obuf + 32 * RS;
+  double** const ptab = reinterpret_cast<double**>(qbuf + 32 * RS);  // row -> field column
+  double** const qtab = ptab + 32;                                   // row -> Q column (null for states)
+  __syncwarp();
+  ptab[lane] = field_ptr(f < m.nf ? f : 0);
+  qtab[lane] = (f >= 3 && f < m.nf) ? Qbase + (size_t)(f - 3) * NLF : nullptr;
+  __syncwarp();
   // cooperative chunk load: element e = i*32 + lane of the [32 rows][CH levels] chunk
   auto prefetch = [&](int chunk) {
     if (chunk < NCHUNK) {
@@ -303,31 +321,28 @@ __global__ void __launch_bounds__(REMAP_MAX_WARPS * 32) remap_kernel(const Remap
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
         const int e = i * 32 + lane, row = e / CH, lev = e % CH, level = chunk * CH + lev;
-        // the row's field pointer is computed by the row's own lane
-        const unsigned long long rp = __shfl_sync(0xffffffffu, (unsigned long long)field_ptr(f < m.nf ? f : 0), row);
-        if (((amask >> row) & 1u) && level < NLEV) cp_async8(dstb + row * RS + lev, (const double*)rp + level);
+        if (((amask >> row) & 1u) && level < NLEV) cp_async8(dstb + row * RS + lev, ptab[row] + level);
       }
     }
     cp_async_commit();
   };
   prefetch(0);
-  prefetch(1);
   // staged raw value of this lane's field at `level` (chunk must have landed)
   auto staged = [&](int level) { return stage[((level / CH) % NBUF) * 32 * RS + lane * RS + level % CH]; };
-  auto chunk_ready = [&](int chunk) {  // before the first read of a chunk: it has landed, refill the ring
-    cp_async_wait<1>();
-    __syncwarp();
-    prefetch(chunk + 2);
-  };
-
   ppm_sweep(
       c, a.alg, active, state,
-      [&](int ln) {  // uniform per step: level ln enters the window
-        if (ln % CH == 0) chunk_ready(ln / CH);
+      [&](int ln) {  // uniform per step: before level ln is read
+        if (ln % CH == 0) {
+          cp_async_wait<0>();  // chunk ln/CH has landed
+          __syncwarp();
+          prefetch(ln / CH + 1);
+        }
       },
       staged,
-      [&](int k, double out) {
-        obuf[lane * RS + k % CH] = out;
+      [&](int k, double out, double over_tgt) {
+        // states leave as x / tgt (ComputeIntrinsicsTag :294-307); tracers as Qdp = x and Q = x / tgt (update_q)
+        obuf[lane * RS + k % CH] = state ? over_tgt : out;
+        qbuf[lane * RS + k % CH] = over_tgt;
         if ((k + 1) % CH == 0 || k + 1 == NLEV) {
           // flush the finished chunk of this column group: its gact lanes store gact rows x CH levels
           const int chunk = k / CH;
@@ -335,15 +350,11 @@ __global__ void __launch_bounds__(REMAP_MAX_WARPS * 32) remap_kernel(const Remap
 #pragma unroll
           for (int i = 0; i < CH; ++i) {
             const int e = i * gact + grank, rowl = e / CH, lev = e % CH, level = chunk * CH + lev;
-            const int row = gfirst + rowl, ff = f - (lane - gfirst) + rowl;  // fields are consecutive in a group
+            const int row = gfirst + rowl;
             if (level < NLEV) {
-              const double val = obuf[row * RS + lev];
-              if (ff < 3) {
-                field_ptr(ff)[level] = div_rcp(val, c.tgt[level], c.rtgt[level]);  // ComputeIntrinsicsTag :294-307
-              } else {
-                field_ptr(ff)[level] = val;
-                Qbase[(size_t)(ff - 3) * NLF + level] = div_rcp(val, c.tgt[level], c.rtgt[level]);  // update_q
-              }
+              ptab[row][level] = obuf[row * RS + lev];
+              double* qp = qtab[row];
+              if (qp) qp[level] = qbuf[row * RS + lev];
             }
           }
           __syncwarp(gmask);
@@ -356,7 +367,7 @@ void vertical_remap(int np1, int np1_qdp) {
   if (!S.nelemd) return;
   RemapArgs a{S.v, S.t, S.dp3d, S.ps_v, S.qdp, S.Q, S.nelemd, np1, np1_qdp, S.p.qsize, S.p.remap_alg, S.invalid_flag};
   const RemapMap m = remap_map(S.p.qsize);
-  const size_t smem = RC * sizeof(ColData) + (size_t)m.nwarps * (NBUF + 1) * 32 * RS * sizeof(double);
+  const size_t smem = RC * sizeof(ColData) + (size_t)m.nwarps * STAGE_PER_WARP * sizeof(double);
   static size_t attr = 0;
   if (smem > attr) {
     CUDA_OK(cudaFuncSetAttribute(remap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -381,6 +392,7 @@ __global__ void __launch_bounds__(64)
     remap_columns_kernel(int alg, int ncols, int nfields, const double* __restrict__ src_dp,
                          const double* __restrict__ tgt_dp, double* __restrict__ fields) {
   __shared__ ColData c;
+  __shared__ double scratch[2 * NLEV + 3];
   const int col = blockIdx.x, lane = threadIdx.x & 31;
   if (threadIdx.x < 32) {
     for (int k = lane; k < NLEV; k += 32) {
@@ -388,12 +400,13 @@ __global__ void __launch_bounds__(64)
       c.tgt[k] = tgt_dp[(size_t)col * NLEV + k];
     }
     __syncwarp();
-    ppm_column_grids(c, lane);
+    ppm_column_grids(c, scratch, lane);
   }
   __syncthreads();
   for (int f = threadIdx.x; f < nfields; f += blockDim.x) {
     double* fld = fields + ((size_t)f * ncols + col) * NLEV;
-    ppm_sweep(c, alg, true, false, [](int) {}, [&](int k) { return fld[k]; }, [&](int k, double x) { fld[k] = x; });
+    ppm_sweep(c, alg, true, false, [](int) {}, [&](int k) { return fld[k]; },
+              [&](int k, double x, double) { fld[k] = x; });
   }
 }
 
