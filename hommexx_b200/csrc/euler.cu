@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(TPB, BIH ? 2 : 4) euler_qminmax_kernel(const E
   int ie, k;
   if (!map_thread(a.nelem, ie, k)) return;
   double* const s_q = s_all + threadIdx.x;  // [2][16][TPB]
-  const double* g = BIH ? s_geo + (ie - e_first) * NPSQ * GEO_N : a.geo;
+  const GeoShared g{s_geo + (BIH ? (ie - e_first) * NPSQ * GEO_N : 0)};
   const int q0 = blockIdx.y * a.qchunk, q1 = min(a.qsize, q0 + a.qchunk);
   const double* const qin = a.qdp + off_q(ie, a.n0_qdp, 0) + k;
   auto prefetch = [&](int q, int buf) {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eule
   double* const s_dpk = s_all + 32 * TPB + tid;
   double* const s_q = s_all + 48 * TPB + tid;
   double* const s_b = s_all + (48 + NPSQ * ADV_NST) * TPB + tid;
-  const double* g = s_geo + (ie - e_first) * NPSQ * GEO_N;
+  const GeoShared g{s_geo + (ie - e_first) * NPSQ * GEO_N};
   const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
   const int q0 = blockIdx.y * a.qchunk, q1 = min(a.qsize, q0 + a.qchunk);
   const double* const qin = a.qdp + off_q(ie, a.n0_qdp, 0) + k;

@@ -3,6 +3,8 @@
 // second Laplacian (TagSecondLaplaceConstHV/TensorHV :92-131) fused with TagHyperPreExchange
 // (:161-257) -> DSS -> TagUpdateStates (:134-158) ].
 // One thread per (element, level), the level's 4x4 planes in registers, no shared memory.
+#include <type_traits>
+
 #include "hxx.cuh"
 
 HXX_DEFINE_CONSTANTS()
@@ -91,7 +93,8 @@ __global__ void __launch_bounds__(TPB, SPONGE ? 2 : 3) hv_second_scalar_kernel(c
   if (!SPONGE) stage_geo<HV2_SPAN, TPB>(s_geo, a.geo, e_first, a.nelem);
   int ie, k;
   if (!map_thread_hv2<SPONGE>(a.nelem, nsponge, ie, k)) return;
-  const double* g = SPONGE ? a.geo + (size_t)ie * NPSQ * GEO_N : s_geo + (ie - e_first) * NPSQ * GEO_N;
+  using Geo = typename std::conditional<SPONGE, GeoGlobal, GeoShared>::type;
+  const Geo g{SPONGE ? a.geo + (size_t)ie * NPSQ * GEO_N : s_geo + (ie - e_first) * NPSQ * GEO_N};
   const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
   const double nst = (k == 0 ? 4.0 : k == 1 ? 2.0 : 1.0) * a.nu_top;  // HyperviscosityFunctorImpl.cpp:24-38
   double s[NPSQ], lap[NPSQ], top[NPSQ];
@@ -144,7 +147,8 @@ __global__ void __launch_bounds__(TPB, 2) hv_second_vector_kernel(const HvArgs a
   if (!SPONGE) stage_geo<HV2_SPAN, TPB>(s_geo, a.geo, e_first, a.nelem);
   int ie, k;
   if (!map_thread_hv2<SPONGE>(a.nelem, nsponge, ie, k)) return;
-  const double* g = SPONGE ? a.geo + (size_t)ie * NPSQ * GEO_N : s_geo + (ie - e_first) * NPSQ * GEO_N;
+  using Geo = typename std::conditional<SPONGE, GeoGlobal, GeoShared>::type;
+  const Geo g{SPONGE ? a.geo + (size_t)ie * NPSQ * GEO_N : s_geo + (ie - e_first) * NPSQ * GEO_N};
   const double* __restrict__ mi = a.metinv + (size_t)ie * 4 * NPSQ;
   const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
   const double* __restrict__ vs = a.consthv ? nullptr : a.vec_sph2cart + (size_t)ie * 6 * NPSQ;

@@ -223,14 +223,20 @@ __device__ __forceinline__ void cp_async_wait() {
 // x / d given r = 1.0 / d (correctly rounded): q = RN(x r) is within one ulp of x/d, the FMA
 // residual e = x - d q is exact, and RN(q + e r) is then the correctly rounded quotient
 // (Markstein). Exactness needs the residual to stay normal, so operands outside a wide safe
-// exponent window (and zeros, infinities, NaNs) take the IEEE division instead. d must be a
-// normal number of moderate magnitude (layer thicknesses, small constants).
+// exponent window take the IEEE division instead (out of line, so that it is never speculated);
+// zeros — common in tracer fields — return x r, the correctly signed zero. d must be a normal
+// number of moderate magnitude (layer thicknesses, small constants).
+static __device__ __noinline__ double div_ieee(double x, double d) { return x / d; }
 __device__ __forceinline__ double div_rcp(double x, double d, double r) {
   const unsigned ex = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
   const double q = x * r;
-  if (ex - 423u > 1200u) return x == 0.0 ? q : x / d;  // x r is the correctly signed zero
   const double e = fma(-d, q, x);
-  return fma(e, r, q);
+  double res = fma(e, r, q);
+  if (ex - 423u > 1200u) {  // zero, denormal, tiny, huge, infinite or NaN
+    res = q;
+    if (x != 0.0) res = div_ieee(x, d);
+  }
+  return res;
 }
 #endif
 

@@ -9,10 +9,21 @@ namespace hxx {
 
 #define HXX_UNROLL _Pragma("unroll")
 
-// g points at the element's geometry record, either in global memory or at the block's copy of
-// it in shared memory (stage_geo below); after inlining the compiler knows which and emits LDG
-// or a shared-memory broadcast load.
-__device__ __forceinline__ double geo_ld(const double* __restrict__ g, int p, int c) { return g[p * GEO_N + c]; }
+// The element's geometry record is read either from global memory through the read-only path
+// (GeoGlobal) or from the block's copy of it in shared memory (GeoShared, see stage_geo). The
+// operators are templates on the accessor so each kernel picks what suits its register budget.
+struct GeoGlobal {
+  const double* __restrict__ p;
+  __device__ __forceinline__ double ld(int i) const { return __ldg(p + i); }
+};
+struct GeoShared {
+  const double* p;
+  __device__ __forceinline__ double ld(int i) const { return p[i]; }
+};
+template <class G>
+__device__ __forceinline__ double geo_ld(const G& g, int p, int c) { return g.ld(p * GEO_N + c); }
+// plain-pointer form (global memory)
+__device__ __forceinline__ double geo_ld(const double* __restrict__ g, int p, int c) { return __ldg(g + p * GEO_N + c); }
 
 // Cooperative copy of the geometry records of the (at most NE) elements a block of the flat
 // (element, level) mapping touches. Every thread of the block must call it (it has a barrier).
@@ -61,7 +72,8 @@ __device__ __forceinline__ void deriv_pair(const double (&sx)[NPSQ], const doubl
 }
 
 // SphereOperators.hpp:293-319
-__device__ __forceinline__ void gradient_sphere(const double* __restrict__ g, const double (&s)[NPSQ],
+template <class G>
+__device__ __forceinline__ void gradient_sphere(const G& g, const double (&s)[NPSQ],
                                                 double (&g0)[NPSQ], double (&g1)[NPSQ]) {
   double dx[NPSQ], dy[NPSQ];
   deriv_pair(s, s, dx, dy);
@@ -74,7 +86,8 @@ __device__ __forceinline__ void gradient_sphere(const double* __restrict__ g, co
 }
 
 // :323-348
-__device__ __forceinline__ void gradient_sphere_update(const double* __restrict__ g, const double (&s)[NPSQ],
+template <class G>
+__device__ __forceinline__ void gradient_sphere_update(const G& g, const double (&s)[NPSQ],
                                                        double (&g0)[NPSQ], double (&g1)[NPSQ]) {
   double dx[NPSQ], dy[NPSQ];
   deriv_pair(s, s, dx, dy);
@@ -87,7 +100,8 @@ __device__ __forceinline__ void gradient_sphere_update(const double* __restrict_
 }
 
 // :352-392
-__device__ __forceinline__ void divergence_sphere(const double* __restrict__ g, const double (&v0)[NPSQ],
+template <class G>
+__device__ __forceinline__ void divergence_sphere(const G& g, const double (&v0)[NPSQ],
                                                   const double (&v1)[NPSQ], double (&div)[NPSQ]) {
   double gv0[NPSQ], gv1[NPSQ];
   HXX_UNROLL
@@ -103,7 +117,8 @@ __device__ __forceinline__ void divergence_sphere(const double* __restrict__ g, 
 }
 
 // :494-533
-__device__ __forceinline__ void vorticity_sphere(const double* __restrict__ g, const double (&u)[NPSQ],
+template <class G>
+__device__ __forceinline__ void vorticity_sphere(const G& g, const double (&u)[NPSQ],
                                                  const double (&v)[NPSQ], double (&vort)[NPSQ]) {
   double c0[NPSQ], c1[NPSQ];
   HXX_UNROLL
@@ -118,7 +133,8 @@ __device__ __forceinline__ void vorticity_sphere(const double* __restrict__ g, c
 }
 
 // :538-583 (inputs are the sphere-basis vector; transformed internally)
-__device__ __forceinline__ void divergence_sphere_wk(const double* __restrict__ g, const double (&v0)[NPSQ],
+template <class G>
+__device__ __forceinline__ void divergence_sphere_wk(const G& g, const double (&v0)[NPSQ],
                                                      const double (&v1)[NPSQ], double (&div)[NPSQ]) {
   double s0[NPSQ], s1[NPSQ];  // spheremp * (Dinv^T v)
   HXX_UNROLL
@@ -143,7 +159,8 @@ __device__ __forceinline__ void divergence_sphere_wk(const double* __restrict__ 
 }
 
 // :588-597
-__device__ __forceinline__ void laplace_simple(const double* __restrict__ g, const double (&s)[NPSQ],
+template <class G>
+__device__ __forceinline__ void laplace_simple(const G& g, const double (&s)[NPSQ],
                                                double (&lap)[NPSQ]) {
   double g0[NPSQ], g1[NPSQ];
   gradient_sphere(g, s, g0, g1);
@@ -151,7 +168,8 @@ __device__ __forceinline__ void laplace_simple(const double* __restrict__ g, con
 }
 
 // :604-635 — tv = this element's tensorVisc [2][2][16]
-__device__ __forceinline__ void laplace_tensor(const double* __restrict__ g, const double* __restrict__ tv,
+template <class G>
+__device__ __forceinline__ void laplace_tensor(const G& g, const double* __restrict__ tv,
                                                const double (&s)[NPSQ], double (&lap)[NPSQ]) {
   double g0[NPSQ], g1[NPSQ], t0[NPSQ], t1[NPSQ];
   gradient_sphere(g, s, g0, g1);
@@ -164,7 +182,8 @@ __device__ __forceinline__ void laplace_tensor(const double* __restrict__ g, con
 }
 
 // :714-748 — mi = this element's metinv [2][2][16]
-__device__ __forceinline__ void grad_sphere_wk_testcov(const double* __restrict__ g, const double* __restrict__ mi,
+template <class G>
+__device__ __forceinline__ void grad_sphere_wk_testcov(const G& g, const double* __restrict__ mi,
                                                        const double (&s)[NPSQ], double (&g0)[NPSQ],
                                                        double (&g1)[NPSQ]) {
   HXX_UNROLL
@@ -193,7 +212,8 @@ __device__ __forceinline__ void grad_sphere_wk_testcov(const double* __restrict_
 }
 
 // :683-710
-__device__ __forceinline__ void curl_sphere_wk_testcov_update(const double* __restrict__ g, double alpha, double beta,
+template <class G>
+__device__ __forceinline__ void curl_sphere_wk_testcov_update(const G& g, double alpha, double beta,
                                                               const double (&s)[NPSQ], double (&c0)[NPSQ],
                                                               double (&c1)[NPSQ]) {
   double ms[NPSQ];
@@ -218,7 +238,8 @@ __device__ __forceinline__ void curl_sphere_wk_testcov_update(const double* __re
 }
 
 // :818-862
-__device__ __forceinline__ void vlaplace_sphere_wk_contra(const double* __restrict__ g, const double* __restrict__ mi,
+template <class G>
+__device__ __forceinline__ void vlaplace_sphere_wk_contra(const G& g, const double* __restrict__ mi,
                                                           double nu_ratio, const double (&v0)[NPSQ],
                                                           const double (&v1)[NPSQ], double (&l0)[NPSQ],
                                                           double (&l1)[NPSQ]) {
@@ -243,7 +264,8 @@ __device__ __forceinline__ void vlaplace_sphere_wk_contra(const double* __restri
 // The same operator with the vector field re-read from memory (level already added to the
 // pointers) for each of its three uses instead of being held in registers across the whole
 // operator: 32 fewer live doubles, and the re-reads hit L1.
-__device__ __forceinline__ void vlaplace_sphere_wk_contra_mem(const double* __restrict__ g, const double* __restrict__ mi,
+template <class G>
+__device__ __forceinline__ void vlaplace_sphere_wk_contra_mem(const G& g, const double* __restrict__ mi,
                                                               double nu_ratio, const double* v0p, const double* v1p,
                                                               double (&l0)[NPSQ], double (&l1)[NPSQ]) {
   double sc[NPSQ];
@@ -275,7 +297,8 @@ __device__ __forceinline__ void vlaplace_sphere_wk_contra_mem(const double* __re
 }
 
 // :752-814 — vs = this element's vec_sph2cart [2][3][16]
-__device__ __forceinline__ void vlaplace_sphere_wk_cartesian(const double* __restrict__ g, const double* __restrict__ tv,
+template <class G>
+__device__ __forceinline__ void vlaplace_sphere_wk_cartesian(const G& g, const double* __restrict__ tv,
                                                              const double* __restrict__ vs, const double (&v0)[NPSQ],
                                                              const double (&v1)[NPSQ], double (&l0)[NPSQ],
                                                              double (&l1)[NPSQ]) {
