@@ -141,13 +141,57 @@ __global__ void __launch_bounds__(TPB, BIH ? 2 : 4) euler_qminmax_kernel(const E
 #define HXX_ADV_MINB_HV 2
 #endif
 constexpr int ADV_NST = HXX_ADV_STAGES;  // staged tracers in flight per thread
-template <bool HV>
-constexpr int advect_slots() { return 48 + NPSQ * ADV_NST * (HV ? 2 : 1); }
+// HV mode of the advection kernel: 0 = no hyperviscosity term; 1 = second Laplacian applied on
+// the fly (one pass less over qtens_biharmonic, but the heaviest register footprint); 2 = the term
+// was prepared in place by euler_hvpost_kernel and is only added here.
+template <int HV>
+constexpr int advect_slots() { return 48 + NPSQ * ADV_NST * (HV == 1 ? 2 : 1); }
+
+// compute_biharmonic_post :216-231 with rhsviss_adjustment :293-310, in place:
+// qtens_biharmonic <- (-rhs_viss dt nu_q) dp0 laplace(qtens_biharmonic) / spheremp
+__global__ void __launch_bounds__(TPB, 3) euler_hvpost_kernel(const EulerArgs a) {
+  extern __shared__ double s_all[];
+  __shared__ double s_geo[geo_span(TPB) * NPSQ * GEO_N];
+  const int e_first = (int)(((long long)blockIdx.x * TPB) / NLEV);
+  stage_geo<geo_span(TPB), TPB>(s_geo, a.geo, e_first, a.nelem);
+  int ie, k;
+  if (!map_thread(a.nelem, ie, k)) return;
+  double* const s_q = s_all + threadIdx.x;  // [2][16][TPB]
+  const GeoShared g{s_geo + (ie - e_first) * NPSQ * GEO_N};
+  const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
+  const int q0 = blockIdx.y * a.qchunk, q1 = min(a.qsize, q0 + a.qchunk);
+  double* const qtb = a.qtens_biharmonic + (size_t)ie * QSIZE_D * NLF + k;
+  auto prefetch = [&](int q, int buf) {
+    if (q < q1) {
+      const double* src = qtb + (size_t)q * NLF;
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) cp_async8(s_q + (buf * NPSQ + p) * TPB, src + p * NLEV);
+    }
+    cp_async_commit();
+  };
+  prefetch(q0, 0);
+  prefetch(q0 + 1, 1);
+  const double dp0k = dc.dp0[k];
+  const double bfac = -a.rhs_viss * a.dt * a.nu_q;
+  for (int q = q0; q < q1; ++q) {
+    const int buf = (q - q0) & 1;
+    cp_async_wait<1>();
+    double s[NPSQ], lap[NPSQ];
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) s[p] = s_q[(buf * NPSQ + p) * TPB];
+    prefetch(q + 2, buf);
+    if (a.consthv) laplace_simple(g, s, lap); else laplace_tensor(g, tv, s, lap);
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) lap[p] = bfac * dp0k * lap[p] / geo_ld(g, p, G_SPHEREMP);
+    plane_store(qtb + (size_t)q * NLF, lap);
+  }
+  cp_async_wait<0>();
+}
 
 // advect_and_limit :317-332 = compute_2d_advection_step (:585-626) + run_tracer_phase (:571-582),
 // with compute_biharmonic_post (:216-231, rhsviss_adjustment :293-310) applied on the fly.
-template <bool HV, bool TAVG>
-__global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) euler_advect_kernel(const EulerArgs a) {
+template <int HV, bool TAVG>
+__global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HXX_ADV_MINB) euler_advect_kernel(const EulerArgs a) {
   extern __shared__ double s_all[];
   __shared__ double s_geo[geo_span(TPB) * NPSQ * GEO_N];
   const int e_first = (int)(((long long)blockIdx.x * TPB) / NLEV);
@@ -170,7 +214,7 @@ __global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eule
       const double* src = qin + (size_t)q * NLF;
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) cp_async8(s_q + (buf * NPSQ + p) * TPB, src + p * NLEV);
-      if (HV) {
+      if (HV == 1) {
         const double* sb = qtb + (size_t)q * NLF;
         HXX_UNROLL
         for (int p = 0; p < NPSQ; ++p) cp_async8(s_b + (buf * NPSQ + p) * TPB, sb + p * NLEV);
@@ -181,7 +225,7 @@ __global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eule
   HXX_UNROLL
   for (int i = 0; i < ADV_NST; ++i) prefetch(q0 + i, i);
 
-  const bool add_ps_diss = a.nu_p > 0 && HV;
+  const bool add_ps_diss = a.nu_p > 0 && HV != 0;
   const double diss_fac = add_ps_diss ? -a.rhs_viss * a.dt * a.nu_q : 0.0;
   double c[NPSQ];
   {
@@ -239,6 +283,8 @@ __global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eule
       const double* pa = a.qdp + off_q(ie, a.tavg_n0, q) + k;
       qa[0] = pa[5 * NLEV]; qa[1] = pa[6 * NLEV]; qa[2] = pa[9 * NLEV]; qa[3] = pa[10 * NLEV];
     }
+    double hvt[NPSQ];
+    if (HV == 2) plane_load(qtb + (size_t)q * NLF, hvt);  // prepared hyperviscosity term, needed after the divergence
     cp_async_wait<ADV_NST - 1>();  // this thread's copies of tracer q have landed
     double x[NPSQ];
     {
@@ -259,7 +305,11 @@ __global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eule
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) x[p] = qd[p] + alpha * ((dx[p] + dy[p]) * geo_ld(g, p, G_RMETDET_R));
     }
-    if (HV) {
+    if (HV == 2) {
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) x[p] += hvt[p];
+    }
+    if (HV == 1) {
       // x is parked in the (already consumed) qdp staging slot while the Laplacian needs registers
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) s_q[(buf * NPSQ + p) * TPB] = x[p];
@@ -361,19 +411,28 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
     minmax_exchange();
   }
   a.qlim = S.qlim;  // minmax_exchange swaps the double buffer
-  const bool hv = S.rhs_viss != 0.0;
-  const size_t smem = (size_t)(hv ? advect_slots<true>() : advect_slots<false>()) * TPB * sizeof(double);
+  static int hv_split = -1;
+  if (hv_split < 0) {
+    const char* e = std::getenv("HXX_HV_SPLIT");
+    hv_split = e ? std::atoi(e) : 1;
+  }
+  const int hv = S.rhs_viss == 0.0 ? 0 : hv_split ? 2 : 1;
+  const size_t smem = (size_t)(hv == 1 ? advect_slots<1>() : advect_slots<0>()) * TPB * sizeof(double);
   static bool attr = false;
   if (!attr) {
-    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 advect_slots<true>() * TPB * (int)sizeof(double)));
-    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 advect_slots<true>() * TPB * (int)sizeof(double)));
-    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 advect_slots<false>() * TPB * (int)sizeof(double)));
-    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 advect_slots<false>() * TPB * (int)sizeof(double)));
+    const int big = advect_slots<1>() * TPB * (int)sizeof(double), small = advect_slots<0>() * TPB * (int)sizeof(double);
+    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
+    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
+    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
+    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
     attr = true;
+  }
+  if (hv == 2) {
+    PROBE(K_EULER_QMINMAX);
+    euler_hvpost_kernel<<<grid, TPB, 2 * (size_t)NPSQ * TPB * sizeof(double), S.stream>>>(a);
+    KERNEL_LAUNCHED(K_EULER_QMINMAX);
   }
   // divdp_proj is both the DSS variable of stage 1 and an input of compute_dp: scale it inside
   // the advection kernel only when its value no longer matters there (rhs_multiplier == 0)
@@ -382,10 +441,12 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   if (separate) a.f_dss = nullptr;
   PROBE(K_EULER_ADVECT);
   const bool tavg = tavg_n0_qdp >= 0;
-  if (hv && tavg) euler_advect_kernel<true, true><<<grid, TPB, smem, S.stream>>>(a);
-  else if (hv) euler_advect_kernel<true, false><<<grid, TPB, smem, S.stream>>>(a);
-  else if (tavg) euler_advect_kernel<false, true><<<grid, TPB, smem, S.stream>>>(a);
-  else euler_advect_kernel<false, false><<<grid, TPB, smem, S.stream>>>(a);
+  if (hv == 1 && tavg) euler_advect_kernel<1, true><<<grid, TPB, smem, S.stream>>>(a);
+  else if (hv == 1) euler_advect_kernel<1, false><<<grid, TPB, smem, S.stream>>>(a);
+  else if (hv == 2 && tavg) euler_advect_kernel<2, true><<<grid, TPB, smem, S.stream>>>(a);
+  else if (hv == 2) euler_advect_kernel<2, false><<<grid, TPB, smem, S.stream>>>(a);
+  else if (tavg) euler_advect_kernel<0, true><<<grid, TPB, smem, S.stream>>>(a);
+  else euler_advect_kernel<0, false><<<grid, TPB, smem, S.stream>>>(a);
   KERNEL_LAUNCHED(K_EULER_ADVECT);
   if (separate) {
     PROBE(K_EULER_FDSS);
