@@ -351,7 +351,7 @@ def main():
         ho.init_dycore()
         ho.run_subcycle()
         t0 = time.perf_counter()
-        nrep = 3
+        nrep = 8
         for _ in range(nrep):
             ho.run_subcycle()
         dt = time.perf_counter() - t0
