@@ -144,8 +144,16 @@ constexpr int ADV_NST = HXX_ADV_STAGES;  // staged tracers in flight per thread
 // HV mode of the advection kernel: 0 = no hyperviscosity term; 1 = second Laplacian applied on
 // the fly (one pass less over qtens_biharmonic, but the heaviest register footprint); 2 = the term
 // was prepared in place by euler_hvpost_kernel and is only added here.
-template <int HV>
-constexpr int advect_slots() { return 48 + NPSQ * ADV_NST * (HV == 1 ? 2 : 1); }
+// shared-memory slots per thread: vstar (2x16) and dpdissk (16), then per staged tracer the qdp
+// plane (16), the qtens_biharmonic / prepared-term plane when HV != 0 (16), the two qlim rows and
+// the four interior time-average partners when TAVG
+template <int HV, bool TAVG>
+__host__ __device__ constexpr int advect_stage_slots() { return NPSQ + (HV ? NPSQ : 0) + 2 + (TAVG ? 4 : 0); }
+template <int HV, bool TAVG>
+__host__ __device__ constexpr int advect_slots() { return 48 + ADV_NST * advect_stage_slots<HV, TAVG>(); }
+#ifndef HXX_ADV_MINB_HV2
+#define HXX_ADV_MINB_HV2 2
+#endif
 
 // compute_biharmonic_post :216-231 with rhsviss_adjustment :293-310, in place:
 // qtens_biharmonic <- (-rhs_viss dt nu_q) dp0 laplace(qtens_biharmonic) / spheremp
@@ -191,7 +199,8 @@ __global__ void __launch_bounds__(TPB, 3) euler_hvpost_kernel(const EulerArgs a)
 // advect_and_limit :317-332 = compute_2d_advection_step (:585-626) + run_tracer_phase (:571-582),
 // with compute_biharmonic_post (:216-231, rhsviss_adjustment :293-310) applied on the fly.
 template <int HV, bool TAVG>
-__global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HXX_ADV_MINB) euler_advect_kernel(const EulerArgs a) {
+__global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HV == 2 ? HXX_ADV_MINB_HV2 : HXX_ADV_MINB)
+    euler_advect_kernel(const EulerArgs a) {
   extern __shared__ double s_all[];
   __shared__ double s_geo[geo_span(TPB) * NPSQ * GEO_N];
   const int e_first = (int)(((long long)blockIdx.x * TPB) / NLEV);
@@ -202,22 +211,37 @@ __global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HXX_ADV_MINB)
   double* const s_vs0 = s_all + tid;
   double* const s_vs1 = s_all + 16 * TPB + tid;
   double* const s_dpk = s_all + 32 * TPB + tid;
-  double* const s_q = s_all + 48 * TPB + tid;
-  double* const s_b = s_all + (48 + NPSQ * ADV_NST) * TPB + tid;
+  constexpr int SS = advect_stage_slots<HV, TAVG>();
+  double* const s_q = s_all + 48 * TPB + tid;               // stage i: slots [i*SS, (i+1)*SS)
+  double* const s_b = s_q + NPSQ * TPB;                     // second plane (HV != 0)
+  double* const s_l = s_q + (HV ? 2 : 1) * NPSQ * TPB;      // qlim rows
+  double* const s_a = s_l + 2 * TPB;                        // time-average partners (TAVG)
   const GeoShared g{s_geo + (ie - e_first) * NPSQ * GEO_N};
   const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
   const int q0 = blockIdx.y * a.qchunk, q1 = min(a.qsize, q0 + a.qchunk);
   const double* const qin = a.qdp + off_q(ie, a.n0_qdp, 0) + k;
   const double* const qtb = a.qtens_biharmonic + (size_t)ie * QSIZE_D * NLF + k;
+  const double* const qlim_in = a.qlim + (size_t)ie * QSIZE_D * 2 * NLEV + k;
+  const double* const qavg = TAVG ? a.qdp + off_q(ie, a.tavg_n0, 0) + k : nullptr;
   auto prefetch = [&](int q, int buf) {
     if (q < q1) {
+      const int o = buf * SS * TPB;
       const double* src = qin + (size_t)q * NLF;
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) cp_async8(s_q + (buf * NPSQ + p) * TPB, src + p * NLEV);
-      if (HV == 1) {
+      for (int p = 0; p < NPSQ; ++p) cp_async8(s_q + o + p * TPB, src + p * NLEV);
+      if (HV) {
         const double* sb = qtb + (size_t)q * NLF;
         HXX_UNROLL
-        for (int p = 0; p < NPSQ; ++p) cp_async8(s_b + (buf * NPSQ + p) * TPB, sb + p * NLEV);
+        for (int p = 0; p < NPSQ; ++p) cp_async8(s_b + o + p * TPB, sb + p * NLEV);
+      }
+      cp_async8(s_l + o, qlim_in + (size_t)q * 2 * NLEV);
+      cp_async8(s_l + o + TPB, qlim_in + (size_t)q * 2 * NLEV + NLEV);
+      if (TAVG) {  // qdp_time_avg :379-403 partner values of the 4 interior points
+        const double* pa = qavg + (size_t)q * NLF;
+        cp_async8(s_a + o, pa + 5 * NLEV);
+        cp_async8(s_a + o + TPB, pa + 6 * NLEV);
+        cp_async8(s_a + o + 2 * TPB, pa + 9 * NLEV);
+        cp_async8(s_a + o + 3 * TPB, pa + 10 * NLEV);
       }
     }
     cp_async_commit();  // possibly empty: keeps one group per loop iteration
@@ -270,27 +294,18 @@ __global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HXX_ADV_MINB)
   const double alpha = -a.dt;
   double* qlp = a.qlim + ((size_t)ie * QSIZE_D + q0) * 2 * NLEV + k;
   double* out = a.qdp + off_q(ie, a.np1_qdp, q0) + k;
-  double qmin_n = qlp[0], qmax_n = qlp[NLEV];
   for (int q = q0; q < q1; ++q, qlp += 2 * NLEV, out += NLF) {
     const int buf = (q - q0) % ADV_NST;
-    const double qmin0 = qmin_n, qmax0 = qmax_n;
-    if (q + 1 < q1) {  // next tracer's bounds, loaded a whole iteration early
-      qmin_n = qlp[2 * NLEV];
-      qmax_n = qlp[3 * NLEV];
-    }
-    double qa[4] = {0.0, 0.0, 0.0, 0.0};
-    if (TAVG) {  // qdp_time_avg :379-403 partner values of the 4 interior points
-      const double* pa = a.qdp + off_q(ie, a.tavg_n0, q) + k;
-      qa[0] = pa[5 * NLEV]; qa[1] = pa[6 * NLEV]; qa[2] = pa[9 * NLEV]; qa[3] = pa[10 * NLEV];
-    }
-    double hvt[NPSQ];
-    if (HV == 2) plane_load(qtb + (size_t)q * NLF, hvt);  // prepared hyperviscosity term, needed after the divergence
+    const int o = buf * SS * TPB;
     cp_async_wait<ADV_NST - 1>();  // this thread's copies of tracer q have landed
+    const double qmin0 = s_l[o], qmax0 = s_l[o + TPB];
+    double qa[4] = {0.0, 0.0, 0.0, 0.0};
+    if (TAVG) { qa[0] = s_a[o]; qa[1] = s_a[o + TPB]; qa[2] = s_a[o + 2 * TPB]; qa[3] = s_a[o + 3 * TPB]; }
     double x[NPSQ];
     {
       double qd[NPSQ], gv0[NPSQ], gv1[NPSQ];
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) qd[p] = s_q[(buf * NPSQ + p) * TPB];
+      for (int p = 0; p < NPSQ; ++p) qd[p] = s_q[o + p * TPB];
       // divergence_sphere_update, SphereOperators.hpp:398-444
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) {
@@ -305,21 +320,21 @@ __global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HXX_ADV_MINB)
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) x[p] = qd[p] + alpha * ((dx[p] + dy[p]) * geo_ld(g, p, G_RMETDET_R));
     }
-    if (HV == 2) {
+    if (HV == 2) {  // the prepared hyperviscosity term
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) x[p] += hvt[p];
+      for (int p = 0; p < NPSQ; ++p) x[p] += s_b[o + p * TPB];
     }
     if (HV == 1) {
       // x is parked in the (already consumed) qdp staging slot while the Laplacian needs registers
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) s_q[(buf * NPSQ + p) * TPB] = x[p];
+      for (int p = 0; p < NPSQ; ++p) s_q[o + p * TPB] = x[p];
       double s[NPSQ], lap[NPSQ];
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) s[p] = s_b[(buf * NPSQ + p) * TPB];
+      for (int p = 0; p < NPSQ; ++p) s[p] = s_b[o + p * TPB];
       if (a.consthv) laplace_simple(g, s, lap); else laplace_tensor(g, tv, s, lap);
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p)
-        x[p] = s_q[(buf * NPSQ + p) * TPB] + bfac * dp0k * lap[p] / geo_ld(g, p, G_SPHEREMP);
+        x[p] = s_q[o + p * TPB] + bfac * dp0k * lap[p] / geo_ld(g, p, G_SPHEREMP);
     }
     prefetch(q + ADV_NST, buf);  // the staged planes of tracer q are in registers now: refill the slot
     // limiter shell :693-761
@@ -417,16 +432,21 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
     hv_split = e ? std::atoi(e) : 1;
   }
   const int hv = S.rhs_viss == 0.0 ? 0 : hv_split ? 2 : 1;
-  const size_t smem = (size_t)(hv == 1 ? advect_slots<1>() : advect_slots<0>()) * TPB * sizeof(double);
+  const bool tavg = tavg_n0_qdp >= 0;
+  auto slots = [&]() {
+    return hv == 1 ? (tavg ? advect_slots<1, true>() : advect_slots<1, false>())
+         : hv == 2 ? (tavg ? advect_slots<2, true>() : advect_slots<2, false>())
+                   : (tavg ? advect_slots<0, true>() : advect_slots<0, false>());
+  };
+  const size_t smem = (size_t)slots() * TPB * sizeof(double);
   static bool attr = false;
   if (!attr) {
-    const int big = advect_slots<1>() * TPB * (int)sizeof(double), small = advect_slots<0>() * TPB * (int)sizeof(double);
-    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
-    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
-    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
-    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
+#define HXX_ADV_ATTR(H, T)                                                                                  \
+  CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               advect_slots<H, T>() * TPB * (int)sizeof(double)))
+    HXX_ADV_ATTR(0, false); HXX_ADV_ATTR(0, true); HXX_ADV_ATTR(1, false); HXX_ADV_ATTR(1, true);
+    HXX_ADV_ATTR(2, false); HXX_ADV_ATTR(2, true);
+#undef HXX_ADV_ATTR
     attr = true;
   }
   if (hv == 2) {
@@ -440,7 +460,6 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   const bool separate = (fdss == S.divdp_proj && a.rhsmdt != 0.0);
   if (separate) a.f_dss = nullptr;
   PROBE(K_EULER_ADVECT);
-  const bool tavg = tavg_n0_qdp >= 0;
   if (hv == 1 && tavg) euler_advect_kernel<1, true><<<grid, TPB, smem, S.stream>>>(a);
   else if (hv == 1) euler_advect_kernel<1, false><<<grid, TPB, smem, S.stream>>>(a);
   else if (hv == 2 && tavg) euler_advect_kernel<2, true><<<grid, TPB, smem, S.stream>>>(a);
