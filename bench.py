@@ -184,7 +184,7 @@ def pin_driver_arrays(h, torch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--ne", type=int, default=0, help="override the mesh (default: 30 at N=1, weak-scaled for N>1)")
