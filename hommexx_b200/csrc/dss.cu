@@ -254,9 +254,11 @@ __global__ void minmax_pack_kernel(const int* __restrict__ send_elem, const doub
   for (int k = threadIdx.x; k < 2 * NLEV; k += blockDim.x) dst[k] = src[k];
 }
 
+// elist = the elements to process (null: all, in order): elements without an off-rank neighbour
+// go first, overlapping the halo exchange the others wait for
 __global__ void minmax_kernel(const int* __restrict__ nbr8, const double* __restrict__ qin, double* __restrict__ qout,
-                              const double* __restrict__ halo, int qsize) {
-  const int ie = blockIdx.x, q = blockIdx.y;
+                              const double* __restrict__ halo, int qsize, const int* __restrict__ elist) {
+  const int ie = elist ? elist[blockIdx.x] : blockIdx.x, q = blockIdx.y;
   for (int k = threadIdx.x; k < NLEV; k += blockDim.x) {
     const double* mine = qin + ((size_t)ie * QSIZE_D + q) * 2 * NLEV;
     double mn = mine[k], mx = mine[NLEV + k];
@@ -290,6 +292,7 @@ void free_exchange_plan() {
   if (S.dss_quads) { cudaFree(S.dss_quads); S.dss_quads = nullptr; }
   S.npairs = S.nquads = 0;
   if (S.nbr8) { cudaFree(S.nbr8); S.nbr8 = nullptr; }
+  if (S.elem_order) { cudaFree(S.elem_order); S.elem_order = nullptr; }
   if (S.send_src) { cudaFree(S.send_src); S.send_src = nullptr; }
   if (S.send_conn_elem) { cudaFree(S.send_conn_elem); S.send_conn_elem = nullptr; }
   if (S.sendbuf) { cudaFree(S.sendbuf); S.sendbuf = nullptr; }
@@ -502,6 +505,25 @@ void build_exchange_plan() {
       if (i.kind == 2) continue;
       nbr8[(size_t)ie * 8 + c] = i.sharing == 0 ? i.r_lid : ~halo_conn_of[(size_t)ie * 8 + c];
     }
+  {
+    // interior elements (no off-rank neighbour) first, then the ones that need the halo
+    std::vector<int> order;
+    order.reserve(n);
+    for (int pass = 0; pass < 2; ++pass)
+      for (int ie = 0; ie < n; ++ie) {
+        bool needs = false;
+        for (int c = 0; c < 8; ++c) needs = needs || (nbr8[(size_t)ie * 8 + c] < 0 && nbr8[(size_t)ie * 8 + c] != DSS_NONE);
+        if (needs == (pass == 1)) order.push_back(ie);
+      }
+    S.n_interior = 0;
+    for (int ie = 0; ie < n; ++ie) {
+      bool needs = false;
+      for (int c = 0; c < 8; ++c) needs = needs || (nbr8[(size_t)ie * 8 + c] < 0 && nbr8[(size_t)ie * 8 + c] != DSS_NONE);
+      if (!needs) ++S.n_interior;
+    }
+    CUDA_OK(cudaMalloc(&S.elem_order, std::max<size_t>(1, order.size()) * sizeof(int)));
+    if (n) CUDA_OK(cudaMemcpy(S.elem_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
   CUDA_OK(cudaMalloc(&S.nbr8, std::max<size_t>(1, nbr8.size()) * sizeof(int)));
   if (n) CUDA_OK(cudaMemcpy(S.nbr8, nbr8.data(), nbr8.size() * sizeof(int), cudaMemcpyHostToDevice));
   if (S.n_send_pts) {
@@ -523,8 +545,8 @@ static void halo_sendrecv(const std::vector<int>& soff, const std::vector<int>& 
   if (!comm) runtime_abort("halo exchange: NCCL communicator not initialised", 13);
   ncclGroupStart();
   for (size_t i = 0; i < S.peer.size(); ++i) {
-    ncclSend(S.sendbuf + (size_t)soff[i] * unit, (size_t)scnt[i] * unit, ncclDouble, S.peer[i], comm, S.stream);
-    ncclRecv(S.recvbuf + (size_t)roff[i] * unit, (size_t)rcnt[i] * unit, ncclDouble, S.peer[i], comm, S.stream);
+    ncclSend(S.sendbuf + (size_t)soff[i] * unit, (size_t)scnt[i] * unit, ncclDouble, S.peer[i], comm, S.comm_stream);
+    ncclRecv(S.recvbuf + (size_t)roff[i] * unit, (size_t)rcnt[i] * unit, ncclDouble, S.peer[i], comm, S.comm_stream);
   }
   if (ncclGroupEnd() != ncclSuccess) runtime_abort("halo exchange: ncclGroupEnd failed", 1);
 #else
@@ -533,12 +555,19 @@ static void halo_sendrecv(const std::vector<int>& soff, const std::vector<int>& 
 #endif
 }
 
+// Overlap: the pack kernel and the NCCL transfers run on the session's communication stream as
+// soon as the producer has finished, while the compute stream does the DSS of every node whose
+// sharers are all on this rank (pair and quad lists — they never touch a packed point); only the
+// generic kernel, which reads the receive buffer, waits for the halo.
 void dss_exchange(const FieldList& fl, bool rspheremp) {
-  if (S.n_send_pts) {
-    PROBE(K_HALO_PACK);
-    halo_pack_kernel<<<dim3(S.n_send_pts, fl.nf), 96, 0, S.stream>>>(S.send_src, S.n_send_pts, fl, S.sendbuf);
+  const bool halo = S.n_send_pts > 0;
+  if (halo) {
+    CUDA_OK(cudaEventRecord(S.ev_produced, S.stream));
+    CUDA_OK(cudaStreamWaitEvent(S.comm_stream, S.ev_produced, 0));
+    halo_pack_kernel<<<dim3(S.n_send_pts, fl.nf), 96, 0, S.comm_stream>>>(S.send_src, S.n_send_pts, fl, S.sendbuf);
     KERNEL_LAUNCHED(K_HALO_PACK);
     halo_sendrecv(S.peer_send_off, S.peer_send_cnt, S.peer_recv_off, S.peer_recv_cnt, (size_t)fl.nf * NLEV);
+    CUDA_OK(cudaEventRecord(S.ev_halo, S.comm_stream));
   }
   const int ny = (fl.nf + DSS_FPB - 1) / DSS_FPB;
   const bool avg = fl.navg > 0;
@@ -559,6 +588,7 @@ void dss_exchange(const FieldList& fl, bool rspheremp) {
     const dim3 grid((unsigned)(((long long)S.nquads * NLEV + DSS_TPB - 1) / DSS_TPB), ny);
     HXX_DSS_LAUNCH(dss_quad_kernel, grid, DSS_TPB, (const DssQuad*)S.dss_quads, S.nquads, fl, S.geo);
   }
+  if (halo) CUDA_OK(cudaStreamWaitEvent(S.stream, S.ev_halo, 0));
   if (S.nnodes) {
     const dim3 grid((S.nnodes + NODES_PB - 1) / NODES_PB, ny);
     HXX_DSS_LAUNCH(dss_nodes_kernel, grid, NODES_PB * NLEV, S.nodes, S.nnodes, fl, S.geo, S.recvbuf);
@@ -576,14 +606,27 @@ void scale_interior_rspheremp(const FieldList& fl) {
 void minmax_exchange() {
   const int nq = S.p.qsize;
   if (!S.nelemd || !nq) return;
-  if (S.n_send_conn) {
-    PROBE(K_HALO_PACK);
-    minmax_pack_kernel<<<dim3(S.n_send_conn, nq), 96, 0, S.stream>>>(S.send_conn_elem, S.qlim, nq, S.sendbuf);
+  const bool halo = S.n_send_conn > 0;
+  if (halo) {
+    CUDA_OK(cudaEventRecord(S.ev_produced, S.stream));
+    CUDA_OK(cudaStreamWaitEvent(S.comm_stream, S.ev_produced, 0));
+    minmax_pack_kernel<<<dim3(S.n_send_conn, nq), 96, 0, S.comm_stream>>>(S.send_conn_elem, S.qlim, nq, S.sendbuf);
     KERNEL_LAUNCHED(K_HALO_PACK);
     halo_sendrecv(S.peer_csend_off, S.peer_csend_cnt, S.peer_crecv_off, S.peer_crecv_cnt, (size_t)nq * 2 * NLEV);
+    CUDA_OK(cudaEventRecord(S.ev_halo, S.comm_stream));
   }
   PROBE(K_MINMAX);
-  minmax_kernel<<<dim3(S.nelemd, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, S.recvbuf, nq);
+  if (!halo) {
+    minmax_kernel<<<dim3(S.nelemd, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, S.recvbuf, nq, nullptr);
+  } else {
+    // elements whose eight neighbours are on this rank first, the others once the halo has landed
+    if (S.n_interior)
+      minmax_kernel<<<dim3(S.n_interior, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, S.recvbuf, nq, S.elem_order);
+    CUDA_OK(cudaStreamWaitEvent(S.stream, S.ev_halo, 0));
+    if (S.nelemd > S.n_interior)
+      minmax_kernel<<<dim3(S.nelemd - S.n_interior, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, S.recvbuf, nq,
+                                                                            S.elem_order + S.n_interior);
+  }
   KERNEL_LAUNCHED(K_MINMAX);
   std::swap(S.qlim, S.qlim_x);
 }

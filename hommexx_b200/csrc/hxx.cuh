@@ -121,7 +121,9 @@ struct Session {
   int rank = 0, nranks = 1, device = 0;
   bool comm_set = false;
   void* nccl = nullptr;  // ncclComm_t
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // compute
+  cudaStream_t comm_stream = nullptr;  // halo pack + NCCL transfers (multi-GPU)
+  cudaEvent_t ev_produced = nullptr, ev_halo = nullptr;
   int64_t launches = 0;
   int64_t launches_by[K_COUNT] = {};
   unsigned long long profile_mask = 0;
@@ -150,6 +152,8 @@ struct Session {
   void *dss_pairs = nullptr, *dss_quads = nullptr;  // lean lists (dss.cu: DssPair / DssQuad)
   int npairs = 0, nquads = 0;
   int* nbr8 = nullptr;  // [nelemd][8] neighbour lid (>=0), ~halo_conn (<0) or DSS_NONE
+  int* elem_order = nullptr;  // local elements, those without an off-rank neighbour first
+  int n_interior = 0;
   // halo (multi-GPU)
   int n_halo_pts = 0;           // receive points (edge = 4, corner = 1 per remote connection)
   int n_send_pts = 0;

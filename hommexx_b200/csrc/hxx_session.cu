@@ -333,6 +333,9 @@ void initialize_hommexx_session(void) {
     runtime_abort(msg, 1);
   }
   CUDA_OK(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&S.comm_stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&S.ev_produced, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&S.ev_halo, cudaEventDisableTiming));
   S.active = true;
   S.launches = 0;
   if (S.rank == 0 && std::getenv("HXX_BANNER"))
@@ -343,12 +346,17 @@ void initialize_hommexx_session(void) {
 void finalize_hommexx_session(void) {
   if (!S.active) return;
   CUDA_OK(cudaStreamSynchronize(S.stream));
+  CUDA_OK(cudaStreamSynchronize(S.comm_stream));
   free_all();
 #ifdef HXX_WITH_NCCL
   if (S.nccl) { ncclCommDestroy((ncclComm_t)S.nccl); S.nccl = nullptr; }
 #endif
   CUDA_OK(cudaStreamDestroy(S.stream));
-  S.stream = nullptr;
+  CUDA_OK(cudaStreamDestroy(S.comm_stream));
+  CUDA_OK(cudaEventDestroy(S.ev_produced));
+  CUDA_OK(cudaEventDestroy(S.ev_halo));
+  S.stream = S.comm_stream = nullptr;
+  S.ev_produced = S.ev_halo = nullptr;
   S.active = false;
   S.comm_set = false;
   S.rank = 0; S.nranks = 1;
