@@ -298,13 +298,16 @@ def main():
     # ---- per-kernel breakdown (untimed extra pass; CUDA events around every launch) ----------
     breakdown = None
     if not args.no_breakdown:
-        lib.hommexx_b200_profile((1 << 19) - 1)
+        nk = 0
+        while lib.hommexx_b200_kernel_name(nk):
+            nk += 1
+        lib.hommexx_b200_profile((1 << nk) - 1)
         lib.hommexx_b200_event_record(2)
         h.run_subcycle()
         lib.hommexx_b200_event_record(3)
         tot = lib.hommexx_b200_event_elapsed_ms(2, 3)
         breakdown = {}
-        for i in range(19):
+        for i in range(nk):
             n = C.c_int64()
             t = lib.hommexx_b200_profile_read(i, C.byref(n))
             if n.value:

@@ -65,7 +65,7 @@ constexpr int EPB = (NLEV * 4 <= 288) ? 4 : 2;
 enum KernelId {
   K_CAAR = 0, K_DSS, K_HALO_PACK, K_RK_COMBINE, K_DP3D_FROM_PS, K_STEP_INIT, K_HV_FIRST, K_HV_SECOND, K_HV_UPDATE,
   K_EULER_DIVDP, K_EULER_QMINMAX, K_MINMAX, K_EULER_ADVECT, K_EULER_FDSS, K_EULER_TAVG, K_REMAP, K_UPDATE_Q,
-  K_TRANSPOSE, K_HOOK, K_COUNT
+  K_TRANSPOSE, K_HOOK, K_FORCING, K_DIAG, K_COUNT
 };
 extern const char* const kernel_names[K_COUNT];
 
@@ -105,7 +105,7 @@ struct Params {  // SimulationParams.hpp
   int remap_alg, limiter_option, rsplit, qsplit, time_step_type, qsize, state_frequency, ftype;
   double nu, nu_p, nu_q, nu_s, nu_div, nu_top, hypervis_scaling, nu_ratio1, nu_ratio2;
   int hypervis_order, hypervis_subcycle;
-  bool moist, disable_diagnostics, consthv, params_set;
+  bool moist, disable_diagnostics, use_cpstar, consthv, params_set;
 };
 
 struct ConnInfo {  // Connectivity.hpp:21-50
@@ -146,6 +146,7 @@ struct Session {
   double *vtens = nullptr, *ttens = nullptr, *dptens = nullptr;
   double *vstar = nullptr, *dpdissk = nullptr, *dp_star = nullptr;  // test-visible scratch
   double *qdp = nullptr, *qtens_biharmonic = nullptr, *qlim = nullptr, *qlim_x = nullptr, *Q = nullptr;
+  double *fm = nullptr, *ft = nullptr, *fq = nullptr;  // CAM forcing [ie][2][16][NLEV], [ie][16][NLEV], [ie][QSIZE_D][16][NLEV]
   // exchange plan
   DssNode* nodes = nullptr;  // generic remainder (cube vertices, nodes with off-rank sharers)
   int nnodes = 0;
@@ -270,6 +271,11 @@ void euler_precompute_divdp();
 // kernel does the interior points, its DSS the boundary nodes)
 void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int dss_opt, int tavg_n0_qdp = -1);
 void euler_qdp_time_avg(int n0_qdp, int np1_qdp);
+// forcing_diag.cu
+void apply_cam_forcing(double dt, bool tracers);  // CamForcing.cpp:149-174 (tracers = false: _dynamics)
+void prim_diag_scalars(bool before_advance, int ivar);
+void prim_energy_halftimes(bool before_advance, int ivar);
+void push_Q_to_host(double* host_q);  // hxx_session.cu: device Q -> F90 layout
 // remap.cu
 void vertical_remap(int np1, int np1_qdp);
 void check_remap_flag();

@@ -29,7 +29,8 @@ void upload_constants() {
 const char* const kernel_names[K_COUNT] = {
     "caar", "dss", "halo_pack", "rk_combine", "dp3d_from_ps", "prim_step_init", "hv_first_laplace",
     "hv_second_laplace_pre_exchange", "hv_update_states", "euler_divdp", "euler_qminmax", "minmax",
-    "euler_advect", "euler_fdss", "euler_time_avg", "remap", "update_q", "transpose", "hook"};
+    "euler_advect", "euler_fdss", "euler_time_avg", "remap", "update_q", "transpose", "hook", "cam_forcing",
+    "diagnostics"};
 
 // ---- per-kernel CUDA-event probes (on the launch stream) -----------------------------------
 namespace {
@@ -137,6 +138,8 @@ static void push_field(const double* dev, double* host, size_t nbatch, int C) {
   }
 }
 
+void push_Q_to_host(double* host_q) { push_field(S.Q, host_q, (size_t)S.nelemd * QSIZE_D, NPSQ); }
+
 static void free_all() {
   dfree(S.geo); dfree(S.metinv); dfree(S.tensorvisc); dfree(S.vec_sph2cart);
   dfree(S.v); dfree(S.t); dfree(S.dp3d); dfree(S.ps_v);
@@ -144,6 +147,7 @@ static void free_all() {
   dfree(S.divdp); dfree(S.divdp_proj); dfree(S.dpdiss_ave); dfree(S.dpdiss_biharmonic);
   dfree(S.vtens); dfree(S.ttens); dfree(S.dptens); dfree(S.vstar); dfree(S.dpdissk); dfree(S.dp_star);
   dfree(S.qdp); dfree(S.qtens_biharmonic); dfree(S.qlim); dfree(S.qlim_x); dfree(S.Q);
+  dfree(S.fm); dfree(S.ft); dfree(S.fq);
   free_exchange_plan();
   dfree(S.invalid_flag);
   if (S.h_invalid) { cudaFreeHost(S.h_invalid); S.h_invalid = nullptr; }
@@ -210,9 +214,10 @@ static bool field_by_name(const char* name, NamedField& out) {
       {"dpdiss_biharmonic", S.dpdiss_biharmonic, f3}, {"qdp", S.qdp, f3 * QNTL * QSIZE_D},
       {"qtens_biharmonic", S.qtens_biharmonic, f3 * QSIZE_D}, {"qlim", S.qlim, ne * QSIZE_D * 2 * NLEV},
       {"Q", S.Q, f3 * QSIZE_D}, {"vtens", S.vtens, f3 * 2}, {"ttens", S.ttens, f3}, {"dptens", S.dptens, f3},
-      {"vstar", S.vstar, f3 * 2}, {"dpdissk", S.dpdissk, f3}, {"dp_star", S.dp_star, f3}};
+      {"vstar", S.vstar, f3 * 2}, {"dpdissk", S.dpdissk, f3}, {"dp_star", S.dp_star, f3},
+      {"fm", S.fm, f3 * 2}, {"ft", S.ft, f3}, {"fq", S.fq, f3 * QSIZE_D}};
   for (const auto& t : tab)
-    if (!std::strcmp(t.nm, name)) { out = t; return true; }
+    if (!std::strcmp(t.nm, name) && t.p) { out = t; return true; }
   return false;
 }
 
@@ -420,7 +425,7 @@ void init_simulation_params_c(const int* remap_alg, const int* limiter_option, c
                               const bool* moisture, const bool* disable_diagnostics, const bool* use_cpstar,
                               const bool* use_semi_lagrangian_transport) {
   const char* loc = "init_simulation_params_c";
-  (void)energy_fixer; (void)use_cpstar;
+  (void)energy_fixer;
   // cxx_f90_interface.cpp:43-52
   if (*remap_alg != 1 && *remap_alg != 2) option_error(loc, "vert_remap_q_alg", *remap_alg);
   if (*prescribed_wind) option_error(loc, "prescribed_wind", 1);
@@ -441,7 +446,7 @@ void init_simulation_params_c(const int* remap_alg, const int* limiter_option, c
   p.nu = *nu; p.nu_p = *nu_p; p.nu_q = *nu_q; p.nu_s = *nu_s; p.nu_div = *nu_div; p.nu_top = *nu_top;
   p.hypervis_order = *hypervis_order; p.hypervis_subcycle = *hypervis_subcycle;
   p.hypervis_scaling = *hypervis_scaling; p.ftype = *ftype;
-  p.moist = *moisture; p.disable_diagnostics = *disable_diagnostics;
+  p.moist = *moisture; p.disable_diagnostics = *disable_diagnostics; p.use_cpstar = *use_cpstar;
   // :88-100
   if (p.nu != p.nu_div) {
     const double ratio = p.nu_div / p.nu;
@@ -554,13 +559,33 @@ void init_time_level_c(const int* nm1, const int* n0, const int* np1, const int*
 
 // prim_driver.cpp:31-156
 void prim_run_subcycle_c(const double* dt, int* nstep, int* nm1, int* n0, int* np1, const int* last_time_step) {
-  (void)last_time_step;
   need_session("prim_run_subcycle_c");
   if (!S.p.params_set) runtime_abort("prim_run_subcycle_c: simulation params not set", 13);
   if (!S.nodes && S.nelemd > 0 && !S.nbr8) runtime_abort("prim_run_subcycle_c: init_boundary_exchanges_c not called", 13);
-  // Diagnostics (:51-64) and CAM forcing (:76-82) are outside the hot path: disable_diagnostics
-  // is .true. in every perf namelist and standalone runs carry zero forcing.
+  const double dt_q = *dt * S.p.qsplit;
+  double dt_remap = dt_q;
+  int nstep_end = S.nstep + S.p.qsplit;
+  if (S.p.rsplit > 0) {
+    dt_remap = dt_q * S.p.rsplit;
+    nstep_end = S.nstep + S.p.qsplit * S.p.rsplit;
+  }
+  // :51-64
+  bool compute_diagnostics =
+      nstep_end % S.p.state_frequency == 0 || nstep_end == S.nstep0 || nstep_end >= *last_time_step;
+  if (S.p.disable_diagnostics) compute_diagnostics = false;
+  if (compute_diagnostics) {
+    update_tracers_levels();
+    prim_diag_scalars(true, 3);
+    prim_energy_halftimes(true, 2);
+  }
   update_tracers_levels();
+  // :76-82 — every standalone namelist has ftype = 0: the pass runs with zero forcing arrays
+  if (S.p.ftype == 0) apply_cam_forcing(dt_remap, true);
+  else if (S.p.ftype == 2) apply_cam_forcing(dt_remap, false);
+  if (compute_diagnostics) {
+    prim_energy_halftimes(true, 0);
+    prim_diag_scalars(true, 0);
+  }
   dp3d_from_ps(S.n0);  // :98-111
   prim_step(*dt);
   for (int r = 1; r < S.p.rsplit; ++r) {
@@ -572,6 +597,10 @@ void prim_run_subcycle_c(const double* dt, int* nstep, int* nm1, int* n0, int* n
   // into its tracer store); without tracers there is nothing to update
   vertical_remap(S.np1, S.np1_qdp);
   check_remap_flag();                // RemapFunctor.hpp:190-198 (one host sync per call)
+  if (compute_diagnostics) {
+    prim_diag_scalars(false, 1);
+    prim_energy_halftimes(false, 1);
+  }
   update_dynamics_levels();
   *nstep = S.nstep; *nm1 = S.nm1; *n0 = S.n0; *np1 = S.np1;
 }
@@ -591,13 +620,33 @@ void cxx_push_results_to_f90(double* const* fv, double* const* ft, double* const
   CUDA_OK(cudaStreamSynchronize(S.stream));
 }
 
+// cxx_f90_interface.cpp:180-205: FM, FT (and FQ when ftype == 0) host -> device; Tracers::push_qdp
+// (Tracers.cpp:46-51) then copies the device qdp back INTO the F90 array
 void f90_push_forcing_to_cxx(double* fm, double* ft, double* fq, double* qdp) {
-  (void)fm; (void)ft; (void)fq; (void)qdp;
-  runtime_abort("f90_push_forcing_to_cxx: CAM forcing is outside the hot path of this build (SURVEY 8f)", 12);
+  need_session("f90_push_forcing_to_cxx");
+  const size_t n = S.nelemd, f3 = n * NLF;
+  if (!S.fm) S.fm = dalloc(f3 * 2);
+  if (!S.ft) S.ft = dalloc(f3);
+  pull_field(fm, S.fm, n, 2 * NPSQ);
+  pull_field(ft, S.ft, n, NPSQ);
+  if (S.p.ftype == 0) {
+    if (!S.fq) S.fq = dalloc(f3 * QSIZE_D);
+    pull_field(fq, S.fq, n * QSIZE_D, NPSQ);
+  }
+  push_field(S.qdp, qdp, n * QNTL * QSIZE_D, NPSQ);
 }
+// cxx_f90_interface.cpp:157-178
 void cxx_push_forcing_to_f90(double* fm, double* ft, double* fq) {
-  (void)fm; (void)ft; (void)fq;
-  runtime_abort("cxx_push_forcing_to_f90: CAM forcing is outside the hot path of this build (SURVEY 8f)", 12);
+  need_session("cxx_push_forcing_to_f90");
+  const size_t n = S.nelemd, f3 = n * NLF;
+  if (!S.fm) S.fm = dalloc(f3 * 2);
+  if (!S.ft) S.ft = dalloc(f3);
+  push_field(S.fm, fm, n, 2 * NPSQ);
+  push_field(S.ft, ft, n, NPSQ);
+  if (S.p.ftype == 0) {
+    if (!S.fq) S.fq = dalloc(f3 * QSIZE_D);
+    push_field(S.fq, fq, n * QSIZE_D, NPSQ);
+  }
 }
 
 // ---- section C: phase-level entry points --------------------------------------------------
@@ -621,6 +670,16 @@ void hxx_vertical_remap(int np1, int np1_qdp, double dt) {
 }
 void hxx_update_q(int np1_qdp, int np1) { update_q(np1_qdp, np1); }
 void hxx_prim_step_init(int n0) { prim_step_init(n0); }
+void hxx_apply_forcing(double dt) {
+  update_tracers_levels();
+  if (S.p.ftype == 0) apply_cam_forcing(dt, true);
+  else if (S.p.ftype == 2) apply_cam_forcing(dt, false);
+}
+void hxx_diagnostics(int before_advance, int ivar_scalars, int ivar_energy) {
+  update_tracers_levels();
+  prim_diag_scalars(before_advance != 0, ivar_scalars);
+  prim_energy_halftimes(before_advance != 0, ivar_energy);
+}
 
 void hxx_exchange(const char* field_set, int rspheremp) {
   FieldList fl;

@@ -181,7 +181,9 @@ struct HommeDriver {
   std::vector<double> D, Dinv, metinv, tensorvisc, vec_sph2cart;
   std::vector<double> fcor, mp, spheremp, rspheremp, metdet, phis, lat, lon, gidf;
   std::vector<double> v, T, dp3d, Qdp, Q, ps_v, omega_p;
-  std::vector<double> accum[7];
+  std::vector<double> accum[7];  // Qvar, Qmass, Q1mass, IEner, IEner_wet, KEner, PEner (elem%accum)
+  std::vector<double> FM, FT, FQ;  // elem%derived%FM/FT/FQ (CAM forcing), Fortran layout
+  int last_step = 1 << 30;         // nEndStep
   std::vector<int> conn;  // add_connection tuples
 
   int nstep = 0, nm1 = 1, n0 = 2, np1 = 3;  // Fortran 1-based time levels
@@ -440,6 +442,9 @@ void jw_init(HommeDriver& h) {
   h.Q.assign((size_t)n * p.qsize_d * nlev * NPSQ, 0.0);
   h.omega_p.assign((size_t)n * nlev * NPSQ, 0.0);
   for (auto& a : h.accum) a.assign((size_t)n * 4 * std::max(1, p.qsize_d) * NPSQ, 0.0);
+  h.FM.assign((size_t)n * nlev * 2 * NPSQ, 0.0);
+  h.FT.assign((size_t)n * nlev * NPSQ, 0.0);
+  h.FQ.assign((size_t)n * p.qsize_d * nlev * NPSQ, 0.0);
   for (int l = 0; l < n; ++l)
     for (int pt = 0; pt < NPSQ; ++pt) {
       const double lat = h.lat[(size_t)l * NPSQ + pt], lon = h.lon[(size_t)l * NPSQ + pt];
@@ -653,7 +658,7 @@ void hd_init_dycore(HommeDriver* h) {
 
 int hd_run_subcycle(HommeDriver* h) {
   // prim_main.F90:300-308
-  const int last = 1 << 30;
+  const int last = h->last_step;
   int nstep_c, nm1_c, n0_c, np1_c;
   get_sym<void (*)(const double*, int*, int*, int*, int*, const int*)>(h, "prim_run_subcycle_c")(
       &h->p.tstep, &nstep_c, &nm1_c, &n0_c, &np1_c, &last);
@@ -667,6 +672,16 @@ void hd_push_results(HommeDriver* h) {
   get_sym<void (*)(double* const*, double* const*, double* const*, double* const*, double* const*,
                    double* const*, double* const*)>(h, "cxx_push_results_to_f90")(&v, &T, &dp, &q, &Q, &ps, &om);
 }
+
+// prim_driver_mod.F90:1380 / :1402 (the CAM-coupled prim_run_subcycle wrapper)
+void hd_push_forcing(HommeDriver* h) {
+  get_sym<void (*)(double*, double*, double*, double*)>(h, "f90_push_forcing_to_cxx")(h->FM.data(), h->FT.data(),
+                                                                                     h->FQ.data(), h->Qdp.data());
+}
+void hd_pull_forcing(HommeDriver* h) {
+  get_sym<void (*)(double*, double*, double*)>(h, "cxx_push_forcing_to_f90")(h->FM.data(), h->FT.data(), h->FQ.data());
+}
+void hd_set_last_step(HommeDriver* h, int nEndStep) { h->last_step = nEndStep; }
 
 void hd_finalize_dycore(HommeDriver* h) { get_sym<void (*)()>(h, "finalize_hommexx_session")(); }
 
@@ -683,6 +698,10 @@ double* hd_array(HommeDriver* h, const char* name, int64_t* n) {
   else if (s == "T") a = &h->T; else if (s == "dp3d") a = &h->dp3d; else if (s == "Qdp") a = &h->Qdp;
   else if (s == "Q") a = &h->Q; else if (s == "ps_v") a = &h->ps_v; else if (s == "omega_p") a = &h->omega_p;
   else if (s == "lat") a = &h->lat; else if (s == "lon") a = &h->lon; else if (s == "gid") a = &h->gidf;
+  else if (s == "FM") a = &h->FM; else if (s == "FT") a = &h->FT; else if (s == "FQ") a = &h->FQ;
+  else if (s == "Qvar") a = &h->accum[0]; else if (s == "Qmass") a = &h->accum[1]; else if (s == "Q1mass") a = &h->accum[2];
+  else if (s == "IEner") a = &h->accum[3]; else if (s == "IEner_wet") a = &h->accum[4];
+  else if (s == "KEner") a = &h->accum[5]; else if (s == "PEner") a = &h->accum[6];
   else if (s == "dvv") { if (n) *n = 16; return &h->gll.dvv[0][0]; }
   if (!a) { if (n) *n = 0; return nullptr; }
   if (n) *n = (int64_t)a->size();

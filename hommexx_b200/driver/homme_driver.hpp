@@ -57,13 +57,19 @@ void hd_upload_state(HommeDriver* h);
 int hd_run_subcycle(HommeDriver* h);
 // cxx_push_results_to_f90 into the driver's Fortran-layout arrays.
 void hd_push_results(HommeDriver* h);
+// CAM-coupling calls of the Fortran prim_run_subcycle wrapper (prim_driver_mod.F90:1380,1402):
+// f90_push_forcing_to_cxx(FM, FT, FQ, Qdp) and cxx_push_forcing_to_f90(FM, FT, FQ).
+void hd_push_forcing(HommeDriver* h);
+void hd_pull_forcing(HommeDriver* h);
+// nEndStep passed to prim_run_subcycle_c as last_time_step (default: never)
+void hd_set_last_step(HommeDriver* h, int nEndStep);
 void hd_finalize_dycore(HommeDriver* h);
 
 // Introspection for tests/bench (pointers stay valid until hd_destroy).
 int hd_nelemd(const HommeDriver* h);
 int hd_nelem_global(const HommeDriver* h);
 // name in {D,Dinv,fcor,mp,spheremp,rspheremp,metdet,metinv,phis,v,T,dp3d,Qdp,Q,ps_v,omega_p,dvv,
-//          lat,lon,gid}; returns element count of the array through *n.
+//          lat,lon,gid,FM,FT,FQ,Qvar,Qmass,Q1mass,IEner,IEner_wet,KEner,PEner}; returns element count of the array through *n.
 double* hd_array(HommeDriver* h, const char* name, int64_t* n);
 // connectivity tuples as passed to add_connection: 8 ints each (all 1-based); returns count.
 int hd_connections(const HommeDriver* h, const int** tuples);

@@ -131,9 +131,11 @@ def driver_lib() -> C.CDLL:
         d.hd_create.restype = C.c_void_p
         d.hd_create.argtypes = [C.POINTER(HommeParams)] + [C.c_void_p] * 4
         for f in ("hd_destroy", "hd_init_jw", "hd_init_dycore", "hd_upload_state", "hd_push_results",
-                  "hd_finalize_dycore"):
+                  "hd_finalize_dycore", "hd_push_forcing", "hd_pull_forcing"):
             getattr(d, f).argtypes = [C.c_void_p]
             getattr(d, f).restype = None
+        d.hd_set_last_step.argtypes = [C.c_void_p, C.c_int]
+        d.hd_set_last_step.restype = None
         d.hd_bind.argtypes = [C.c_void_p, C.c_char_p]
         d.hd_bind.restype = C.c_int
         d.hd_last_error.restype = C.c_char_p
@@ -170,6 +172,10 @@ def load_dycore(path) -> C.CDLL:
     lib.hxx_vertical_remap.argtypes = [C.c_int, C.c_int, C.c_double]
     lib.hxx_update_q.argtypes = [C.c_int, C.c_int]
     lib.hxx_prim_step_init.argtypes = [C.c_int]
+    lib.hxx_apply_forcing.argtypes = [C.c_double]
+    lib.hxx_apply_forcing.restype = None
+    lib.hxx_diagnostics.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.hxx_diagnostics.restype = None
     lib.hxx_exchange.argtypes = [C.c_char_p, C.c_int]
     lib.hxx_get_field.argtypes = [C.c_char_p, C.c_void_p]
     lib.hxx_get_field.restype = C.c_int64
@@ -228,6 +234,33 @@ class Homme:
 
     def push_results(self):
         self.d.hd_push_results(self.h)
+
+    def push_forcing(self):
+        """f90_push_forcing_to_cxx(FM, FT, FQ, Qdp): forcing arrays to the dycore, Qdp back to the driver."""
+        self.d.hd_push_forcing(self.h)
+
+    def pull_forcing(self):
+        self.d.hd_pull_forcing(self.h)
+
+    def set_last_step(self, n_end_step: int):
+        self.d.hd_set_last_step(self.h, n_end_step)
+
+    def forcing(self) -> dict:
+        c, n = self.cfg, self.nelemd
+        return {"FM": self.array("FM").reshape(n, c.nlev, 2, 4, 4), "FT": self.array("FT").reshape(n, c.nlev, 4, 4),
+                "FQ": self.array("FQ").reshape(n, c.qsize_d, c.nlev, 4, 4)}
+
+    def accum(self) -> dict:
+        """elem%accum diagnostics written by the dycore (Diagnostics.cpp:17-35 shapes)."""
+        c, n = self.cfg, self.nelemd
+        qd = max(1, c.qsize_d)
+        out = {}
+        for nm, shp in (("Qvar", (4, qd, 4, 4)), ("Qmass", (4, qd, 4, 4)), ("Q1mass", (qd, 4, 4)),
+                        ("IEner", (4, 4, 4)), ("IEner_wet", (4, 4)), ("KEner", (4, 4, 4)), ("PEner", (4, 4, 4))):
+            a = self.array(nm)
+            k = int(np.prod(shp))
+            out[nm] = a[: n * k].reshape((n,) + shp)
+        return out
 
     def finalize(self):
         if self._initialised:

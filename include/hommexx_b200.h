@@ -149,6 +149,12 @@ void hxx_vertical_remap(int np1, int np1_qdp, double dt);
 void hxx_update_q(int np1_qdp, int np1);
 /* prim_step's zeroing kernel, prim_step.cpp:51-66 */
 void hxx_prim_step_init(int n0);
+/* apply_cam_forcing (ftype 0) / apply_cam_forcing_dynamics (ftype 2), CamForcing.cpp:149-174, on
+ * time level n0 / n0_qdp with the FM, FT, FQ last pushed by f90_push_forcing_to_cxx */
+void hxx_apply_forcing(double dt);
+/* Diagnostics::prim_diag_scalars + prim_energy_halftimes, Diagnostics.cpp:37-185, into the arrays
+ * registered with init_diagnostics_c */
+void hxx_diagnostics(int before_advance, int ivar_scalars, int ivar_energy);
 /* BoundaryExchange::exchange on a named field set: "caar:<tl>", "hv", "euler:<np1_qdp>:<dssopt>",
  * "qtens", and exchange_min_max for "qlim". rspheremp!=0 applies the inverse mass afterwards. */
 void hxx_exchange(const char* field_set, int rspheremp);
@@ -157,7 +163,7 @@ void hxx_exchange(const char* field_set, int rspheremp);
  * [nelemd][...][np][np][nlev]; returns the number of doubles (0 if the name is unknown).
  * Names: v t dp3d ps_v phi omega_p eta_dot_dpdn derived_vn0 derived_dp divdp divdp_proj
  *        dpdiss_ave dpdiss_biharmonic qdp qtens_biharmonic qlim Q vtens ttens dptens
- *        vstar dpdissk dp_star */
+ *        vstar dpdissk dp_star fm ft fq */
 int64_t hxx_get_field(const char* name, double* out);
 int64_t hxx_set_field(const char* name, const double* in);
 

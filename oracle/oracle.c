@@ -59,7 +59,7 @@ static struct Oracle {
   int remap_alg, limiter_option, rsplit, qsplit, time_step_type, qsize, state_frequency, ftype;
   double nu, nu_p, nu_q, nu_s, nu_div, nu_top, hypervis_scaling, nu_ratio1, nu_ratio2;
   int hypervis_order, hypervis_subcycle;
-  bool moist, disable_diagnostics, consthv, params_set;
+  bool moist, disable_diagnostics, use_cpstar, consthv, params_set;
   /* TimeLevel.hpp */
   int nm1, n0, np1, nstep, nstep0, n0_qdp, np1_qdp;
   /* Derivative / HybridVCoord */
@@ -77,6 +77,9 @@ static struct Oracle {
   /* Tracers: qdp [ie][2][qsize_d][16][nlev]; qtens_biharmonic, Q [ie][qsize_d][16][nlev];
      qlim [ie][qsize_d][2][nlev] */
   double *qdp, *qtens_biharmonic, *qlim, *Q;
+  /* CAM forcing (Elements.hpp m_fm, m_ft; Tracers.hpp fq): fm [ie][2][16][nlev], ft [ie][16][nlev],
+     fq [ie][qsize_d][16][nlev] */
+  double *fm, *ft, *fq;
   /* euler step data */
   double rhs_viss;
   /* Connectivity */
@@ -137,7 +140,7 @@ static void free_all(void) {
                      &O.t, &O.dp3d, &O.ps_v, &O.phi, &O.omega_p, &O.eta_dot_dpdn, &O.derived_vn0,
                      &O.derived_dp, &O.divdp, &O.divdp_proj, &O.dpdiss_ave, &O.dpdiss_biharmonic, &O.vtens,
                      &O.ttens, &O.dptens, &O.vstar, &O.dpdissk, &O.dp_star, &O.qdp, &O.qtens_biharmonic,
-                     &O.qlim, &O.Q};
+                     &O.qlim, &O.Q, &O.fm, &O.ft, &O.fq};
   for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i) {
     free(*ptrs[i]);
     *ptrs[i] = NULL;
@@ -213,7 +216,7 @@ void init_simulation_params_c(const int* remap_alg, const int* limiter_option, c
                               const bool* moisture, const bool* disable_diagnostics, const bool* use_cpstar,
                               const bool* use_semi_lagrangian_transport) {
   const char* loc = "init_simulation_params_c";
-  (void)energy_fixer; (void)use_cpstar;
+  (void)energy_fixer;
   /* cxx_f90_interface.cpp:43-52 */
   if (*remap_alg != 1 && *remap_alg != 2) option_error(loc, "vert_remap_q_alg", *remap_alg);
   if (*prescribed_wind) option_error(loc, "prescribed_wind", 1);
@@ -230,7 +233,7 @@ void init_simulation_params_c(const int* remap_alg, const int* limiter_option, c
   O.nu = *nu; O.nu_p = *nu_p; O.nu_q = *nu_q; O.nu_s = *nu_s; O.nu_div = *nu_div; O.nu_top = *nu_top;
   O.hypervis_order = *hypervis_order; O.hypervis_subcycle = *hypervis_subcycle;
   O.hypervis_scaling = *hypervis_scaling; O.ftype = *ftype;
-  O.moist = *moisture; O.disable_diagnostics = *disable_diagnostics;
+  O.moist = *moisture; O.disable_diagnostics = *disable_diagnostics; O.use_cpstar = *use_cpstar;
   /* :88-100 */
   if (O.nu != O.nu_div) {
     const double ratio = O.nu_div / O.nu;
@@ -286,6 +289,7 @@ void init_elements_2d_c(const int* num_elems, const double* const* D, const doub
   O.vstar = zalloc(f3 * 2); O.dpdissk = zalloc(f3); O.dp_star = zalloc(f3);
   O.qdp = zalloc(f3 * QNTL * O.qsize_d); O.qtens_biharmonic = zalloc(f3 * O.qsize_d);
   O.Q = zalloc(f3 * O.qsize_d); O.qlim = zalloc((size_t)n * O.qsize_d * 2 * nl);
+  O.fm = zalloc(f3 * 2); O.ft = zalloc(f3); O.fq = zalloc(f3 * O.qsize_d);
 }
 
 /* SyncUtils.hpp: F90 [ie][tl][lev][(2)][igp][jgp]  <->  [ie][tl][(2)][igp][jgp][lev] */
@@ -353,13 +357,48 @@ void cxx_push_results_to_f90(double* const* fv, double* const* ft, double* const
       for (int p = 0; p < NPSQ; ++p) (*fom)[((size_t)ie * nl + k) * NPSQ + p] = O.omega_p[F3(ie) + p * nl + k];
 }
 
+/* cxx_f90_interface.cpp:180-205: FM [ie][nlev][2][16], FT [ie][nlev][16], FQ [ie][qsize_d][nlev][16] (F90) to the
+   device layout; FQ only for ftype == 0 (FORCING_DEBUG); Tracers::push_qdp (Tracers.cpp:46-51) copies the
+   device qdp back INTO the F90 array */
 void f90_push_forcing_to_cxx(double* fm, double* ft, double* fq, double* qdp) {
-  (void)fm; (void)ft; (void)fq; (void)qdp;
-  runtime_abort("oracle: CAM forcing is outside the hot path (SURVEY 8f)", 12);
+  const int n = O.nelemd, nl = O.nlev;
+  for (int ie = 0; ie < n; ++ie)
+    for (int k = 0; k < nl; ++k)
+      for (int p = 0; p < NPSQ; ++p) {
+        O.ft[F3(ie) + p * nl + k] = ft[((size_t)ie * nl + k) * NPSQ + p];
+        for (int c = 0; c < 2; ++c)
+          O.fm[((size_t)ie * 2 + c) * NLF + p * nl + k] = fm[(((size_t)ie * nl + k) * 2 + c) * NPSQ + p];
+      }
+  if (O.ftype == 0)
+    for (int ie = 0; ie < n; ++ie)
+      for (int q = 0; q < O.qsize_d; ++q)
+        for (int k = 0; k < nl; ++k)
+          for (int p = 0; p < NPSQ; ++p)
+            O.fq[((size_t)ie * O.qsize_d + q) * NLF + p * nl + k] = fq[(((size_t)ie * O.qsize_d + q) * nl + k) * NPSQ + p];
+  for (int ie = 0; ie < n; ++ie)
+    for (int tq = 0; tq < QNTL; ++tq)
+      for (int q = 0; q < O.qsize_d; ++q)
+        for (int k = 0; k < nl; ++k)
+          for (int p = 0; p < NPSQ; ++p)
+            qdp[((((size_t)ie * QNTL + tq) * O.qsize_d + q) * nl + k) * NPSQ + p] =
+                O.qdp[(((size_t)ie * QNTL + tq) * O.qsize_d + q) * NLF + p * nl + k];
 }
+/* cxx_f90_interface.cpp:157-178 */
 void cxx_push_forcing_to_f90(double* fm, double* ft, double* fq) {
-  (void)fm; (void)ft; (void)fq;
-  runtime_abort("oracle: CAM forcing is outside the hot path (SURVEY 8f)", 12);
+  const int n = O.nelemd, nl = O.nlev;
+  for (int ie = 0; ie < n; ++ie)
+    for (int k = 0; k < nl; ++k)
+      for (int p = 0; p < NPSQ; ++p) {
+        ft[((size_t)ie * nl + k) * NPSQ + p] = O.ft[F3(ie) + p * nl + k];
+        for (int c = 0; c < 2; ++c)
+          fm[(((size_t)ie * nl + k) * 2 + c) * NPSQ + p] = O.fm[((size_t)ie * 2 + c) * NLF + p * nl + k];
+      }
+  if (O.ftype == 0)
+    for (int ie = 0; ie < n; ++ie)
+      for (int q = 0; q < O.qsize_d; ++q)
+        for (int k = 0; k < nl; ++k)
+          for (int p = 0; p < NPSQ; ++p)
+            fq[(((size_t)ie * O.qsize_d + q) * nl + k) * NPSQ + p] = O.fq[((size_t)ie * O.qsize_d + q) * NLF + p * nl + k];
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -1474,17 +1513,167 @@ static void prim_step(double dt) {
   if (O.qsize > 0) prim_advec_tracers_remap_RK2(dt * O.qsplit);
 }
 
+/* CamForcing.cpp:20-49 state_forcing */
+static void state_forcing(int np1, double dt) {
+#pragma omp parallel for
+  for (int ie = 0; ie < O.nelemd; ++ie) {
+    double* t = TFLD(ie, np1);
+    const double* ft = O.ft + F3(ie);
+    for (size_t i = 0; i < NLF; ++i) t[i] += dt * ft[i];
+    for (int c = 0; c < 2; ++c) {
+      double* v = VFLD(ie, np1, c);
+      const double* fm = O.fm + ((size_t)ie * 2 + c) * NLF;
+      for (size_t i = 0; i < NLF; ++i) v[i] += dt * fm[i];
+    }
+  }
+}
+
+/* CamForcing.cpp:51-147 tracer_forcing (np1 = tl.n0, np1_qdp = tl.n0_qdp) */
+static void tracer_forcing(double dt) {
+  const int nlev = O.nlev, np1 = O.n0, np1_qdp = O.n0_qdp;
+#pragma omp parallel for
+  for (int ie = 0; ie < O.nelemd; ++ie) {
+    double* ps = O.ps_v + ((size_t)ie * NTL + np1) * NPSQ;
+    if (O.moist) { /* :65-108, reads qdp before the update below */
+      const double* fq0 = O.fq + (size_t)ie * O.qsize_d * NLF;
+      const double* q0 = QDPFLD(ie, np1_qdp, 0);
+      for (int p = 0; p < NPSQ; ++p) {
+        double acc = 0.0;
+        for (int k = 0; k < nlev; ++k) {
+          double v1 = dt * fq0[IX(p, k)];
+          const double qs = q0[IX(p, k)];
+          if (qs + v1 < 0.0 && v1 < 0.0) v1 = qs < 0.0 ? 0.0 : -qs;
+          acc += v1;
+        }
+        ps[p] += acc;
+      }
+    }
+    for (int q = 0; q < O.qsize; ++q) { /* :110-131 */
+      const double* fq = O.fq + ((size_t)ie * O.qsize_d + q) * NLF;
+      double* qd = QDPFLD(ie, np1_qdp, q);
+      for (size_t i = 0; i < NLF; ++i) {
+        double v1 = dt * fq[i];
+        if (qd[i] + v1 < 0.0 && v1 < 0.0) v1 = qd[i] < 0.0 ? 0.0 : -qd[i];
+        qd[i] += v1;
+      }
+    }
+    for (int q = 0; q < O.qsize; ++q) { /* :133-146 */
+      const double* qd = QDPFLD(ie, np1_qdp, q);
+      double* Q = O.Q + ((size_t)ie * O.qsize_d + q) * NLF;
+      for (int p = 0; p < NPSQ; ++p)
+        for (int k = 0; k < nlev; ++k) {
+          const double dp = O.dai[k] * O.ps0 + O.dbi[k] * ps[p];
+          Q[IX(p, k)] = qd[IX(p, k)] / dp;
+        }
+    }
+  }
+}
+
+/* CamForcing.cpp:149-174 */
+static void apply_cam_forcing(double dt) {
+  state_forcing(O.n0, dt);
+  tracer_forcing(dt);
+}
+static void apply_cam_forcing_dynamics(double dt) { state_forcing(O.n0, dt); }
+
+/* Diagnostics.cpp:37-90. diag[] = {Q, Qvar, Qmass, Q1mass, IEner, IEner_wet, KEner, PEner} (F90-owned):
+   Q [ie][qsize_d][nlev][16]; Qvar, Qmass [ie][4][qsize_d][16]; Q1mass [ie][qsize_d][16];
+   IEner, KEner, PEner [ie][4][16]; IEner_wet [ie][16] */
+static void prim_diag_scalars(bool before_advance, int ivar) {
+  const int nlev = O.nlev, qd_ = O.qsize_d;
+  update_tracers_levels();
+  const int t2_qdp = before_advance ? O.n0_qdp : O.np1_qdp;
+  if (O.time_step_type <= 0) return;
+  double *hQ = O.diag[0], *Qvar = O.diag[1], *Qmass = O.diag[2], *Q1mass = O.diag[3];
+  for (int ie = 0; ie < O.nelemd; ++ie) /* sync_to_host(tracers.Q, h_Q): all QSIZE_D tracers */
+    for (int q = 0; q < qd_; ++q)
+      for (int k = 0; k < nlev; ++k)
+        for (int p = 0; p < NPSQ; ++p)
+          hQ[(((size_t)ie * qd_ + q) * nlev + k) * NPSQ + p] = O.Q[((size_t)ie * qd_ + q) * NLF + IX(p, k)];
+  for (int ie = 0; ie < O.nelemd; ++ie)
+    for (int q = 0; q < O.qsize; ++q) {
+      const double* qdp = QDPFLD(ie, t2_qdp, q);
+      for (int p = 0; p < NPSQ; ++p) {
+        double accum_qdp_q = 0, accum_qdp = 0;
+        for (int k = 0; k < nlev; ++k) {
+          accum_qdp_q += qdp[IX(p, k)] * hQ[(((size_t)ie * qd_ + q) * nlev + k) * NPSQ + p];
+          accum_qdp += qdp[IX(p, k)];
+        }
+        Qvar[(((size_t)ie * 4 + ivar) * qd_ + q) * NPSQ + p] = accum_qdp_q;
+        Qmass[(((size_t)ie * 4 + ivar) * qd_ + q) * NPSQ + p] = accum_qdp;
+        Q1mass[((size_t)ie * qd_ + q) * NPSQ + p] = accum_qdp;
+      }
+    }
+}
+
+/* Diagnostics.cpp:92-185 */
+static void prim_energy_halftimes(bool before_advance, int ivar) {
+  const int nlev = O.nlev;
+  const double cp = 1005.0, cpwv = 1870.0; /* PhysicalConstants.hpp */
+  update_tracers_levels();
+  const int t1 = before_advance ? O.n0 : O.np1, t1_qdp = before_advance ? O.n0_qdp : O.np1_qdp;
+  double *IE = O.diag[4], *IEw = O.diag[5], *KE = O.diag[6], *PE = O.diag[7];
+  for (int ie = 0; ie < O.nelemd; ++ie)
+    for (int p = 0; p < NPSQ; ++p) {
+      double IEner = 0.0, IEner_wet = 0.0, KEner = 0.0, PEner = 0.0;
+      const double *u = VFLD(ie, t1, 0), *v = VFLD(ie, t1, 1), *T = TFLD(ie, t1);
+      const double ps = O.ps_v[((size_t)ie * NTL + t1) * NPSQ + p], phis = S2(O.phis, ie, p);
+      for (int k = 0; k < nlev; ++k) {
+        const double dpt1 = O.dai[k] * O.ps0 + O.dbi[k] * ps;
+        double cp_star1 = cp;
+        if (O.use_cpstar) {
+          const double qval = QDPFLD(ie, t1_qdp, 0)[IX(p, k)] / dpt1;
+          cp_star1 = cp * (1.0 + (cpwv / cp - 1.0) * qval);
+        }
+        IEner += cp_star1 * T[IX(p, k)] * dpt1;
+        IEner_wet += (cp_star1 - cp) * T[IX(p, k)] * dpt1;
+        KEner += (u[IX(p, k)] * u[IX(p, k)] + v[IX(p, k)] * v[IX(p, k)]) * 0.5 * dpt1;
+        PEner += phis * dpt1;
+      }
+      IE[((size_t)ie * 4 + ivar) * NPSQ + p] = IEner;
+      IEw[(size_t)ie * NPSQ + p] = IEner_wet;
+      KE[((size_t)ie * 4 + ivar) * NPSQ + p] = KEner;
+      PE[((size_t)ie * 4 + ivar) * NPSQ + p] = PEner;
+    }
+}
+
+void hxx_apply_forcing(double dt) {
+  update_tracers_levels();
+  if (O.ftype == 0) apply_cam_forcing(dt);
+  else if (O.ftype == 2) apply_cam_forcing_dynamics(dt);
+}
+void hxx_diagnostics(int before_advance, int ivar_scalars, int ivar_energy) {
+  prim_diag_scalars(before_advance != 0, ivar_scalars);
+  prim_energy_halftimes(before_advance != 0, ivar_energy);
+}
+
 /* prim_driver.cpp:31-156 */
 void prim_run_subcycle_c(const double* dt, int* nstep, int* nm1, int* n0, int* np1, const int* last_time_step) {
-  (void)last_time_step;
   const int nlev = O.nlev;
   if (!O.params_set) runtime_abort("prim_run_subcycle_c: simulation params not set", 13);
   const double dt_q = *dt * O.qsplit;
   double dt_remap = dt_q;
-  if (O.rsplit > 0) dt_remap = dt_q * O.rsplit;
-  /* diagnostics are outside the hot path (disable_diagnostics=.true. in every perf namelist) */
+  int nstep_end = O.nstep + O.qsplit;
+  if (O.rsplit > 0) {
+    dt_remap = dt_q * O.rsplit;
+    nstep_end = O.nstep + O.qsplit * O.rsplit;
+  }
+  /* :51-64 */
+  bool compute_diagnostics =
+      nstep_end % O.state_frequency == 0 || nstep_end == O.nstep0 || nstep_end >= *last_time_step;
+  if (O.disable_diagnostics) compute_diagnostics = false;
+  if (compute_diagnostics) {
+    prim_diag_scalars(true, 3);
+    prim_energy_halftimes(true, 2);
+  }
   update_tracers_levels();
-  /* ftype==0 forcing with zero FM/FT/FQ leaves the state unchanged (CamForcing.cpp:20-147) */
+  /* :76-82: standalone runs carry ftype = 0 with zero FM/FT/FQ, and still take this pass */
+  if (O.ftype == 0) apply_cam_forcing(dt_remap);
+  else if (O.ftype == 2) apply_cam_forcing_dynamics(dt_remap);
+  if (compute_diagnostics) {
+    prim_energy_halftimes(true, 0);
+    prim_diag_scalars(true, 0);
+  }
   /* dp3d from ps_v :98-111 */
 #pragma omp parallel for
   for (int ie = 0; ie < O.nelemd; ++ie) {
@@ -1501,6 +1690,10 @@ void prim_run_subcycle_c(const double* dt, int* nstep, int* nm1, int* n0, int* n
   update_tracers_levels();
   hxx_vertical_remap(O.np1, O.np1_qdp, dt_remap);
   hxx_update_q(O.np1_qdp, O.np1);
+  if (compute_diagnostics) {
+    prim_diag_scalars(false, 1);
+    prim_energy_halftimes(false, 1);
+  }
   update_dynamics_levels();
   *nstep = O.nstep; *nm1 = O.nm1; *n0 = O.n0; *np1 = O.np1;
 }
@@ -1547,7 +1740,8 @@ static double* field_by_name(const char* name, size_t* n) {
       {"dpdiss_biharmonic", O.dpdiss_biharmonic, f3}, {"qdp", O.qdp, f3 * QNTL * O.qsize_d},
       {"qtens_biharmonic", O.qtens_biharmonic, f3 * O.qsize_d}, {"qlim", O.qlim, ne * O.qsize_d * 2 * O.nlev},
       {"Q", O.Q, f3 * O.qsize_d}, {"vtens", O.vtens, f3 * 2}, {"ttens", O.ttens, f3}, {"dptens", O.dptens, f3},
-      {"vstar", O.vstar, f3 * 2}, {"dpdissk", O.dpdissk, f3}, {"dp_star", O.dp_star, f3}};
+      {"vstar", O.vstar, f3 * 2}, {"dpdissk", O.dpdissk, f3}, {"dp_star", O.dp_star, f3},
+      {"fm", O.fm, f3 * 2}, {"ft", O.ft, f3}, {"fq", O.fq, f3 * O.qsize_d}};
   for (size_t i = 0; i < sizeof(tab) / sizeof(tab[0]); ++i)
     if (!strcmp(tab[i].nm, name)) { *n = tab[i].n; return tab[i].p; }
   *n = 0;
