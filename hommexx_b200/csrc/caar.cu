@@ -42,11 +42,15 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
   extern __shared__ double sm[];
   double* s_p = sm;                  // dp -> pressure
   double* s_x = sm + E * NPSQ * LS;  // div_vdp -> running sum; then a_k -> phi
+  __shared__ double s_geo[E * NPSQ * GEO_N];
   const int tid = threadIdx.x, e = tid / NLEV, k = tid % NLEV;
+  // the block's geometry records: every operator below re-reads them, and shared-memory reads do
+  // not queue behind the block's outstanding HBM requests
+  stage_geo<E, E * NLEV>(s_geo, a.geo, blockIdx.x * E, a.nelem);
   int ie = blockIdx.x * E + e;
   const bool valid = ie < a.nelem;
   if (!valid) ie = a.nelem - 1;
-  const double* __restrict__ g = a.geo + (size_t)ie * NPSQ * GEO_N;
+  const GeoShared g{s_geo + (valid ? e : 0) * NPSQ * GEO_N};
   const double* v0p = a.v + off_v(ie, a.n0, 0) + k;
   const double* v1p = a.v + off_v(ie, a.n0, 1) + k;
   const int col0 = e * NPSQ;
@@ -61,13 +65,20 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) { v0[p] *= dp[p]; v1[p] *= dp[p]; }
     if (a.eta_ave_w != 0.0 && valid) {
+      // every read-modify-write and every nm1 -> np1 update below loads its whole plane before the
+      // first store: a store between two loads of possibly aliasing arrays would serialise them
       double* n0p = a.vn0 + ((size_t)ie * 2 + 0) * NLF + k;
       double* n1p = a.vn0 + ((size_t)ie * 2 + 1) * NLF + k;
+      double a0[NPSQ], a1[NPSQ];
+      plane_load(n0p, a0);
+      plane_load(n1p, a1);
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) {
-        n0p[p * NLEV] += a.eta_ave_w * v0[p];
-        n1p[p * NLEV] += a.eta_ave_w * v1[p];
+        a0[p] += a.eta_ave_w * v0[p];
+        a1[p] += a.eta_ave_w * v1[p];
       }
+      plane_store(n0p, a0);
+      plane_store(n1p, a1);
     }
     divergence_sphere(g, v0, v1, div);
   }
@@ -130,20 +141,20 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
   }
   // compute_dp3d_np1 :468-493 (eta_dot_dpdn == 0 for rsplit > 0); stored now, dp/div die here
   if (valid) {
-    const double* dm = a.dp3d + off_s(ie, a.nm1) + k;
-    double* dn = a.dp3d + off_s(ie, a.np1) + k;
+    double r[NPSQ];
+    plane_load(a.dp3d + off_s(ie, a.nm1) + k, r);
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {
-      double r = geo_ld(g, p, G_SPHEREMP) * (dm[p * NLEV] - div[p] * a.dt);
-      if (a.fold_rsp && is_interior_pt(p)) r *= geo_ld(g, p, G_RSPHEREMP);
-      dn[p * NLEV] = r;
+      r[p] = geo_ld(g, p, G_SPHEREMP) * (r[p] - div[p] * a.dt);
+      if (a.fold_rsp && is_interior_pt(p)) r[p] *= geo_ld(g, p, G_RSPHEREMP);
     }
+    plane_store(a.dp3d + off_s(ie, a.np1) + k, r);
   }
   __syncthreads();
   if (tid < E * NPSQ) {
     double* cx = s_x + tid * LS;
     const int iec = min(blockIdx.x * E + tid / NPSQ, a.nelem - 1);
-    const double phis = a.geo[((size_t)iec * NPSQ + (tid % NPSQ)) * GEO_N + G_PHIS];
+    const double phis = s_geo[((iec - blockIdx.x * E) * NPSQ + (tid % NPSQ)) * GEO_N + G_PHIS];
     double integ = 0.0;
     for (int k0 = NLEV - 1; k0 >= 0; k0 -= 8) {
       double ak[8];
@@ -171,23 +182,25 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
   }
   if (a.eta_ave_w != 0.0 && valid) {  // compute_omega_p :412-423
     double* om = a.omega_p + off_f(ie) + k;
+    double r[NPSQ];
+    plane_load(om, r);
     HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) om[p * NLEV] += a.eta_ave_w * omega[p];
+    for (int p = 0; p < NPSQ; ++p) r[p] += a.eta_ave_w * omega[p];
+    plane_store(om, r);
   }
   {  // compute_temperature_np1 :430-463
-    double tg0[NPSQ], tg1[NPSQ];
+    double tg0[NPSQ], tg1[NPSQ], r[NPSQ];
+    plane_load(a.t + off_s(ie, a.nm1) + k, r);
     gradient_sphere(g, tn0, tg0, tg1);
-    const double* tm = a.t + off_s(ie, a.nm1) + k;
-    double* tp = a.t + off_s(ie, a.np1) + k;
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {
       const double vgrad_t = v0[p] * tg0[p] + v1[p] * tg1[p];
       const double ttens = -vgrad_t + kappa * tv[p] * omega[p];
-      double r = ttens * a.dt + tm[p * NLEV];
-      r *= geo_ld(g, p, G_SPHEREMP);
-      if (a.fold_rsp && is_interior_pt(p)) r *= geo_ld(g, p, G_RSPHEREMP);
-      if (valid) tp[p * NLEV] = r;
+      r[p] = ttens * a.dt + r[p];
+      r[p] *= geo_ld(g, p, G_SPHEREMP);
+      if (a.fold_rsp && is_interior_pt(p)) r[p] *= geo_ld(g, p, G_RSPHEREMP);
     }
+    if (valid) plane_store(a.t + off_s(ie, a.np1) + k, r);
   }
   // compute_velocity_np1 :184-232 with compute_energy_grad :98-132
   {
@@ -204,19 +217,17 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
     gradient_sphere_update(g, ephi, g0, g1);
   }
   {
-    double vort[NPSQ];
+    double vort[NPSQ], r0[NPSQ], r1[NPSQ];
+    plane_load(a.v + off_v(ie, a.nm1, 0) + k, r0);
+    plane_load(a.v + off_v(ie, a.nm1, 1) + k, r1);
     vorticity_sphere(g, v0, v1, vort);
-    const double* vm0 = a.v + off_v(ie, a.nm1, 0) + k;
-    const double* vm1 = a.v + off_v(ie, a.nm1, 1) + k;
-    double* vp0 = a.v + off_v(ie, a.np1, 0) + k;
-    double* vp1 = a.v + off_v(ie, a.np1, 1) + k;
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {
       const double vt = vort[p] + geo_ld(g, p, G_FCOR);
       double e0 = -g0[p] + v1[p] * vt;
       double e1 = -g1[p] - v0[p] * vt;
-      e0 = e0 * a.dt + vm0[p * NLEV];
-      e1 = e1 * a.dt + vm1[p * NLEV];
+      e0 = e0 * a.dt + r0[p];
+      e1 = e1 * a.dt + r1[p];
       const double sm_ = geo_ld(g, p, G_SPHEREMP);
       e0 = sm_ * e0;
       e1 = sm_ * e1;
@@ -225,10 +236,12 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
         e0 *= rs;
         e1 *= rs;
       }
-      if (valid) {
-        vp0[p * NLEV] = e0;
-        vp1[p * NLEV] = e1;
-      }
+      r0[p] = e0;
+      r1[p] = e1;
+    }
+    if (valid) {
+      plane_store(a.v + off_v(ie, a.np1, 0) + k, r0);
+      plane_store(a.v + off_v(ie, a.np1, 1) + k, r1);
     }
   }
 }

@@ -81,17 +81,31 @@ __global__ void __launch_bounds__(TPB, BIH ? 2 : 4) euler_qminmax_kernel(const E
   };
   prefetch(q0, 0);
   prefetch(q0 + 1, 1);
-  double dps[NPSQ], dave[NPSQ];
+  // dp of compute_dp, its reciprocal and (hyperviscosity stage) dpdiss_ave are the same for every
+  // tracer: the BIH instantiation parks them in per-thread shared-memory slots [32 + 16][TPB] behind
+  // the staging buffers so that its Laplacian has the registers, the other one keeps them in registers
+  double* const s_dp = s_q + 2 * NPSQ * TPB;
+  double* const s_rdp = s_dp + NPSQ * TPB;
+  double* const s_dave = s_rdp + NPSQ * TPB;
+  double dps[BIH ? 1 : NPSQ];
+  const bool scale = BIH && a.nu_p > 0;
   {
     double r0[NPSQ], r1[NPSQ];
     plane_load(a.derived_dp + off_f(ie) + k, r0);
     plane_load(a.divdp_proj + off_f(ie) + k, r1);
     HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) dps[p] = r0[p] - a.rhsmdt * r1[p];
+    for (int p = 0; p < NPSQ; ++p) {
+      const double d = r0[p] - a.rhsmdt * r1[p];
+      if constexpr (BIH) { s_dp[p * TPB] = d; s_rdp[p * TPB] = 1.0 / d; }
+      else dps[p] = d;
+    }
+    if (scale) {
+      plane_load(a.dpdiss_ave + off_f(ie) + k, r0);
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) s_dave[p * TPB] = r0[p];
+    }
   }
-  const bool scale = BIH && a.nu_p > 0;
-  if (scale) plane_load(a.dpdiss_ave + off_f(ie) + k, dave);
-  const double dp0k = dc.dp0[k];
+  const double dp0k = dc.dp0[k], rdp0k = 1.0 / dp0k;
   double* ql = a.qlim + ((size_t)ie * QSIZE_D + q0) * 2 * NLEV + k;
   double* qtb = a.qtens_biharmonic + ((size_t)ie * QSIZE_D + q0) * NLF + k;
   double mn_n = 0.0, mx_n = 0.0;
@@ -106,7 +120,10 @@ __global__ void __launch_bounds__(TPB, BIH ? 2 : 4) euler_qminmax_kernel(const E
     for (int p = 0; p < NPSQ; ++p) Q[p] = s_q[(buf * NPSQ + p) * TPB];
     prefetch(q + 2, buf);
     HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) Q[p] = Q[p] / dps[p];
+    for (int p = 0; p < NPSQ; ++p) {
+      if constexpr (BIH) Q[p] = div_rcp(Q[p], s_dp[p * TPB], s_rdp[p * TPB]);
+      else Q[p] = Q[p] / dps[p];
+    }
     if (a.rhs_mode != 1) { mn = Q[0]; mx = Q[0]; }
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) { mn = fmin(mn, Q[p]); mx = fmax(mx, Q[p]); }
@@ -116,7 +133,7 @@ __global__ void __launch_bounds__(TPB, BIH ? 2 : 4) euler_qminmax_kernel(const E
       double lap[NPSQ];
       if (scale) {
         HXX_UNROLL
-        for (int p = 0; p < NPSQ; ++p) Q[p] = Q[p] * dave[p] / dp0k;
+        for (int p = 0; p < NPSQ; ++p) Q[p] = div_rcp(Q[p] * s_dave[p * TPB], dp0k, rdp0k);
       }
       laplace_simple(g, Q, lap);
       HXX_UNROLL
@@ -190,7 +207,8 @@ __global__ void __launch_bounds__(TPB, 3) euler_hvpost_kernel(const EulerArgs a)
     prefetch(q + 2, buf);
     if (a.consthv) laplace_simple(g, s, lap); else laplace_tensor(g, tv, s, lap);
     HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) lap[p] = bfac * dp0k * lap[p] / geo_ld(g, p, G_SPHEREMP);
+    for (int p = 0; p < NPSQ; ++p)
+      lap[p] = div_rcp(bfac * dp0k * lap[p], geo_ld(g, p, G_SPHEREMP), geo_ld(g, p, G_INV_SPHEREMP));
     plane_store(qtb + (size_t)q * NLF, lap);
   }
   cp_async_wait<0>();
@@ -334,7 +352,7 @@ __global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HV == 2 ? HXX
       if (a.consthv) laplace_simple(g, s, lap); else laplace_tensor(g, tv, s, lap);
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p)
-        x[p] = s_q[o + p * TPB] + bfac * dp0k * lap[p] / geo_ld(g, p, G_SPHEREMP);
+        x[p] = s_q[o + p * TPB] + div_rcp(bfac * dp0k * lap[p], geo_ld(g, p, G_SPHEREMP), geo_ld(g, p, G_INV_SPHEREMP));
     }
     prefetch(q + ADV_NST, buf);  // the staged planes of tracer q are in registers now: refill the slot
     // limiter shell :693-761
@@ -413,7 +431,13 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   PROBE(K_EULER_QMINMAX);
   {
     constexpr size_t smem_mm = 2 * (size_t)NPSQ * TPB * sizeof(double);
-    if (mode == 2) euler_qminmax_kernel<true><<<grid, TPB, smem_mm, S.stream>>>(a);
+    constexpr size_t smem_bih = 5 * (size_t)NPSQ * TPB * sizeof(double);
+    static bool attr_mm = false;
+    if (!attr_mm) {
+      CUDA_OK(cudaFuncSetAttribute(euler_qminmax_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bih));
+      attr_mm = true;
+    }
+    if (mode == 2) euler_qminmax_kernel<true><<<grid, TPB, smem_bih, S.stream>>>(a);
     else euler_qminmax_kernel<false><<<grid, TPB, smem_mm, S.stream>>>(a);
   }
   KERNEL_LAUNCHED(K_EULER_QMINMAX);

@@ -119,12 +119,22 @@ __global__ void __launch_bounds__(TPB, SPONGE ? 2 : 3) hv_second_scalar_kernel(c
     plane_load(dt_, s);
     if (a.consthv) laplace_simple(g, s, lap); else laplace_tensor(g, tv, s, lap);
     plane_load(a.dp3d + off_s(ie, a.np1) + k, dp);
-    double* dave = a.dpdiss_ave + off_f(ie) + k;
-    double* dbih = a.dpdiss_biharmonic + off_f(ie) + k;
-    HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) {
-      dave[p * NLEV] += a.eta_ave_w * dp[p] / a.hypervis_subcycle;
-      dbih[p * NLEV] += a.eta_ave_w * lap[p] / a.hypervis_subcycle;
+    {
+      // whole planes are loaded before the first store (a store between two loads of possibly
+      // aliasing arrays would serialise them); the subcycle count divides through its reciprocal
+      double* dave = a.dpdiss_ave + off_f(ie) + k;
+      double* dbih = a.dpdiss_biharmonic + off_f(ie) + k;
+      double r0[NPSQ], r1[NPSQ];
+      plane_load(dave, r0);
+      plane_load(dbih, r1);
+      const double hs = (double)a.hypervis_subcycle, rhs = 1.0 / hs;
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) {
+        r0[p] += div_rcp(a.eta_ave_w * dp[p], hs, rhs);
+        r1[p] += div_rcp(a.eta_ave_w * lap[p], hs, rhs);
+      }
+      plane_store(dave, r0);
+      plane_store(dbih, r1);
     }
     if (SPONGE) laplace_simple(g, dp, top);
     HXX_UNROLL

@@ -54,7 +54,8 @@ enum {
   G_DINV00 = 0, G_DINV01, G_DINV10, G_DINV11,  // Dinv(a,b) at the point
   G_D00, G_D01, G_D10, G_D11,                  // D(a,b)
   G_METDET, G_RMETDET_R,                       // metdet, (1/metdet)*rrearth
-  G_SPHEREMP, G_RSPHEREMP, G_FCOR, G_PHIS, G_MP, G_PAD,
+  G_SPHEREMP, G_RSPHEREMP, G_FCOR, G_PHIS, G_MP,
+  G_INV_SPHEREMP,                              // 1 / spheremp (NOT rspheremp, the assembled inverse mass)
   GEO_N
 };
 

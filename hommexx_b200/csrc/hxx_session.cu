@@ -501,6 +501,7 @@ void init_elements_2d_c(const int* num_elems, const double* const* D, const doub
       g[G_FCOR] = (*fcor)[s];
       g[G_PHIS] = (*phis)[s];
       g[G_MP] = (*mp)[s];
+      g[G_INV_SPHEREMP] = 1.0 / (*spheremp)[s];
     }
   S.geo = dalloc(geo.size());
   CUDA_OK(cudaMemcpyAsync(S.geo, geo.data(), geo.size() * 8, cudaMemcpyHostToDevice, S.stream));
