@@ -42,6 +42,9 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
   extern __shared__ double sm[];
   double* s_p = sm;                  // dp -> pressure
   double* s_x = sm + E * NPSQ * LS;  // div_vdp -> running sum; then a_k -> phi
+  double* s_y = sm + 2 * E * NPSQ * LS;
+  double* s_z = sm + 3 * E * NPSQ * LS;
+  double* s_w = sm + 4 * E * NPSQ * LS;
   __shared__ double s_geo[E * NPSQ * GEO_N];
   const int tid = threadIdx.x, e = tid / NLEV, k = tid % NLEV;
   // the block's geometry records: every operator below re-reads them, and shared-memory reads do
@@ -116,28 +119,31 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
   }
   __syncthreads();
 
-  double pr[NPSQ], tv[NPSQ], tn0[NPSQ];
-  plane_load(a.t + off_s(ie, a.n0) + k, tn0);
-  if (a.n0_qdp < 0) {  // :333-344
-    HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) tv[p] = tn0[p];
-  } else {  // :348-363
-    const double* q = a.qdp + off_q(ie, a.n0_qdp, 0) + k;
+  // From here on the planes that outlive a phase are parked in shared memory, in the column-major
+  // slots the scans use (thread (e, k) owns [col0 + p][k]): s_p pressure, s_x the hydrostatic
+  // integrand -> phi, s_y the omega integral -> omega, s_z virtual temperature. Registers then hold
+  // five planes at most, which is what keeps the kernel out of local memory.
+  {
+    double tv[NPSQ];
+    plane_load(a.t + off_s(ie, a.n0) + k, tv);
+    if (a.n0_qdp >= 0) {  // :348-363 (dry: Tv = T, :333-344)
+      double q[NPSQ];
+      plane_load(a.qdp + off_q(ie, a.n0_qdp, 0) + k, q);
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) {
+        double Qt = q[p] / dp[p];
+        Qt *= (Rwater_vapor / Rgas - 1.0);
+        Qt += 1.0;
+        tv[p] = tv[p] * Qt;
+      }
+    }
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {
-      double Qt = q[p * NLEV] / dp[p];
-      Qt *= (Rwater_vapor / Rgas - 1.0);
-      Qt += 1.0;
-      tv[p] = tn0[p] * Qt;
+      const int slot = (col0 + p) * LS + k;
+      s_y[slot] = s_x[slot] + 0.5 * div[p];  // integration + 0.5*div_vdp of preq_omega_ps
+      s_x[slot] = Rgas * tv[p] * (dp[p] * 0.5 / s_p[slot]);  // preq_hydrostatic :689-729
+      s_z[slot] = tv[p];
     }
-  }
-  double sint[NPSQ];  // integration + 0.5*div_vdp of preq_omega_ps
-  HXX_UNROLL
-  for (int p = 0; p < NPSQ; ++p) {
-    const int slot = (col0 + p) * LS + k;
-    pr[p] = s_p[slot];
-    sint[p] = s_x[slot] + 0.5 * div[p];
-    s_x[slot] = Rgas * tv[p] * (dp[p] * 0.5 / pr[p]);  // preq_hydrostatic :689-729
   }
   // compute_dp3d_np1 :468-493 (eta_dot_dpdn == 0 for rsplit > 0); stored now, dp/div die here
   if (valid) {
@@ -171,63 +177,79 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
   }
   __syncthreads();
 
-  double v0[NPSQ], v1[NPSQ], omega[NPSQ], g0[NPSQ], g1[NPSQ];
+  // Each operator below keeps its input plane in registers and finishes one point at a time, so a
+  // result goes to its slot (or to HBM) as soon as it exists.
+  double v0[NPSQ], v1[NPSQ];
   plane_load(v0p, v0);
   plane_load(v1p, v1);
-  gradient_sphere(g, pr, g0, g1);  // grad p
-  HXX_UNROLL
-  for (int p = 0; p < NPSQ; ++p) {
-    const double vgrad_p = v0[p] * g0[p] + v1[p] * g1[p];
-    omega[p] = (vgrad_p - sint[p]) / pr[p];
+  {
+    double pr[NPSQ];
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) pr[p] = s_p[(col0 + p) * LS + k];
+    phase_fence();
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) {
+      const int slot = (col0 + p) * LS + k;
+      double g0, g1;
+      gradient_point(g, pr, p, g0, g1);  // grad p
+      const double vgrad_p = v0[p] * g0 + v1[p] * g1;
+      s_y[slot] = (vgrad_p - s_y[slot]) / pr[p];  // omega
+      const double r = Rgas * (s_z[slot] / pr[p]);  // compute_energy_grad :98-132
+      s_p[slot] = r * g0;  // the pressure is in registers: its slot and the next plane take the gradient
+      s_w[slot] = r * g1;
+    }
   }
+  phase_fence();
   if (a.eta_ave_w != 0.0 && valid) {  // compute_omega_p :412-423
     double* om = a.omega_p + off_f(ie) + k;
     double r[NPSQ];
     plane_load(om, r);
     HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) r[p] += a.eta_ave_w * omega[p];
+    for (int p = 0; p < NPSQ; ++p) r[p] += a.eta_ave_w * s_y[(col0 + p) * LS + k];
     plane_store(om, r);
   }
-  {  // compute_temperature_np1 :430-463
-    double tg0[NPSQ], tg1[NPSQ], r[NPSQ];
-    plane_load(a.t + off_s(ie, a.nm1) + k, r);
-    gradient_sphere(g, tn0, tg0, tg1);
-    HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) {
-      const double vgrad_t = v0[p] * tg0[p] + v1[p] * tg1[p];
-      const double ttens = -vgrad_t + kappa * tv[p] * omega[p];
-      r[p] = ttens * a.dt + r[p];
-      r[p] *= geo_ld(g, p, G_SPHEREMP);
-      if (a.fold_rsp && is_interior_pt(p)) r[p] *= geo_ld(g, p, G_RSPHEREMP);
-    }
-    if (valid) plane_store(a.t + off_s(ie, a.np1) + k, r);
-  }
-  // compute_velocity_np1 :184-232 with compute_energy_grad :98-132
+  phase_fence();
+  // compute_velocity_np1 :184-232
   {
     double ephi[NPSQ];
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {
-      const double r = Rgas * (tv[p] / pr[p]);
-      g0[p] = r * g0[p];
-      g1[p] = r * g1[p];
       const double phi = s_x[(col0 + p) * LS + k];
       if (a.store_phi && valid) a.phi[off_f(ie) + p * NLEV + k] = phi;
       ephi[p] = 0.5 * (v0[p] * v0[p] + v1[p] * v1[p]) + phi;
     }
-    gradient_sphere_update(g, ephi, g0, g1);
+    phase_fence();
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) {  // gradient_sphere_update
+      const int slot = (col0 + p) * LS + k;
+      double g0, g1;
+      gradient_point(g, ephi, p, g0, g1);
+      s_p[slot] += g0;
+      s_w[slot] += g1;
+    }
   }
+  phase_fence();
   {
-    double vort[NPSQ], r0[NPSQ], r1[NPSQ];
-    plane_load(a.v + off_v(ie, a.nm1, 0) + k, r0);
-    plane_load(a.v + off_v(ie, a.nm1, 1) + k, r1);
-    vorticity_sphere(g, v0, v1, vort);
+    double c0[NPSQ], c1[NPSQ];  // vorticity_sphere :494-533, one point at a time
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {
-      const double vt = vort[p] + geo_ld(g, p, G_FCOR);
-      double e0 = -g0[p] + v1[p] * vt;
-      double e1 = -g1[p] - v0[p] * vt;
-      e0 = e0 * a.dt + r0[p];
-      e1 = e1 * a.dt + r1[p];
+      c0[p] = geo_ld(g, p, G_D00) * v0[p] + geo_ld(g, p, G_D01) * v1[p];
+      c1[p] = geo_ld(g, p, G_D10) * v0[p] + geo_ld(g, p, G_D11) * v1[p];
+    }
+    const double* vm0 = a.v + off_v(ie, a.nm1, 0) + k;
+    const double* vm1 = a.v + off_v(ie, a.nm1, 1) + k;
+    double* s_o0 = s_x;  // phi is dead: its slot takes the second velocity component
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) {
+      const int slot = (col0 + p) * LS + k;
+      double dvdx, dudy;
+      deriv_point(c1, c0, p / NP, p % NP, dvdx, dudy);
+      const double vort = (dvdx - dudy) * geo_ld(g, p, G_RMETDET_R);
+      const double vt = vort + geo_ld(g, p, G_FCOR);
+      double e0 = -s_p[slot] + v1[p] * vt;
+      double e1 = -s_w[slot] - v0[p] * vt;
+      e0 = e0 * a.dt + vm0[p * NLEV];
+      e1 = e1 * a.dt + vm1[p * NLEV];
       const double sm_ = geo_ld(g, p, G_SPHEREMP);
       e0 = sm_ * e0;
       e1 = sm_ * e1;
@@ -236,13 +258,37 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
         e0 *= rs;
         e1 *= rs;
       }
-      r0[p] = e0;
-      r1[p] = e1;
+      s_p[slot] = e0;  // to HBM after the loop: a store to v(np1) between the loads of v(nm1) would
+      s_o0[slot] = e1; // serialise them (the two may alias as far as the compiler knows)
     }
+    phase_fence();
     if (valid) {
-      plane_store(a.v + off_v(ie, a.np1, 0) + k, r0);
-      plane_store(a.v + off_v(ie, a.np1, 1) + k, r1);
+      double* vp0 = a.v + off_v(ie, a.np1, 0) + k;
+      double* vp1 = a.v + off_v(ie, a.np1, 1) + k;
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) {
+        vp0[p * NLEV] = s_p[(col0 + p) * LS + k];
+        vp1[p * NLEV] = s_o0[(col0 + p) * LS + k];
+      }
     }
+  }
+  phase_fence();
+  {  // compute_temperature_np1 :430-463
+    double tn0[NPSQ], r[NPSQ];
+    plane_load(a.t + off_s(ie, a.n0) + k, tn0);
+    plane_load(a.t + off_s(ie, a.nm1) + k, r);
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) {
+      const int slot = (col0 + p) * LS + k;
+      double tg0, tg1;
+      gradient_point(g, tn0, p, tg0, tg1);
+      const double vgrad_t = v0[p] * tg0 + v1[p] * tg1;
+      const double ttens = -vgrad_t + kappa * s_z[slot] * s_y[slot];
+      r[p] = ttens * a.dt + r[p];
+      r[p] *= geo_ld(g, p, G_SPHEREMP);
+      if (a.fold_rsp && is_interior_pt(p)) r[p] *= geo_ld(g, p, G_RSPHEREMP);
+    }
+    if (valid) plane_store(a.t + off_s(ie, a.np1) + k, r);
   }
 }
 
@@ -250,7 +296,7 @@ void caar_run(int nm1, int n0, int np1, double dt, double eta_ave_w, int n0_qdp,
   if (!S.nelemd) return;
   CaarArgs a{S.geo, S.v, S.t, S.dp3d, S.derived_vn0, S.omega_p, S.phi, S.qdp, S.nelemd, nm1, n0, np1, n0_qdp,
              dt, eta_ave_w, with_dss ? 1 : 0, S.store_phi ? 1 : 0};
-  constexpr size_t smem = 2 * (size_t)CAAR_E * NPSQ * (NLEV + 1) * sizeof(double);
+  constexpr size_t smem = 5 * (size_t)CAAR_E * NPSQ * (NLEV + 1) * sizeof(double);
   static bool attr = false;
   if (!attr) {
     CUDA_OK(cudaFuncSetAttribute(caar_kernel<CAAR_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

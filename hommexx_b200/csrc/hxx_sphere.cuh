@@ -71,6 +71,30 @@ __device__ __forceinline__ void deriv_pair(const double (&sx)[NPSQ], const doubl
   }
 }
 
+// one point of deriv_pair (same sums, same order)
+__device__ __forceinline__ void deriv_point(const double (&sx)[NPSQ], const double (&sy)[NPSQ], int i, int j, double& a,
+                                            double& b) {
+  a = dc.dvv[j][0] * sx[i * NP + 0];
+  b = dc.dvv[i][0] * sy[0 * NP + j];
+  HXX_UNROLL
+  for (int m = 1; m < NP; ++m) {
+    a += dc.dvv[j][m] * sx[i * NP + m];
+    b += dc.dvv[i][m] * sy[m * NP + j];
+  }
+}
+// one point of gradient_sphere (:293-319)
+template <class G>
+__device__ __forceinline__ void gradient_point(const G& g, const double (&s)[NPSQ], int p, double& g0, double& g1) {
+  double dx, dy;
+  deriv_point(s, s, p / NP, p % NP, dx, dy);
+  const double v0 = dx * rrearth, v1 = dy * rrearth;
+  g0 = geo_ld(g, p, G_DINV00) * v0 + geo_ld(g, p, G_DINV01) * v1;
+  g1 = geo_ld(g, p, G_DINV10) * v0 + geo_ld(g, p, G_DINV11) * v1;
+}
+// compiler-level fence: keeps loads and stores (and with them the live ranges they start or end) on
+// their side of a phase boundary
+__device__ __forceinline__ void phase_fence() { asm volatile("" ::: "memory"); }
+
 // SphereOperators.hpp:293-319
 template <class G>
 __device__ __forceinline__ void gradient_sphere(const G& g, const double (&s)[NPSQ],

@@ -7,7 +7,8 @@ out=gpurun_out
 mkdir -p $out
 rep=/tmp/${tag}
 timeout 1200 ncu --set full --clock-control none --import-source on \
-  --kernel-name regex:"caar_kernel|hv_first|hv_second|hv_update|euler_qminmax|euler_hvpost|euler_advect|minmax_kernel|remap_kernel|dss_pair|dss_quad" \
+  --kernel-name regex:"${NCU_REGEX:-caar_kernel|hv_first|hv_second|hv_update|euler_qminmax|euler_hvpost|euler_advect|minmax_kernel|remap_kernel|dss_pair|dss_quad}" \
+  ${NCU_SKIP:+--launch-skip $NCU_SKIP} \
   ${NCU_COUNT:+-c $NCU_COUNT} -f -o $rep python scripts/prof_step.py ${PROF_ARGS} > $out/${tag}.log 2>&1
 tail -2 $out/${tag}.log
 ncu -i $rep.ncu-rep --page raw --csv > $out/${tag}_raw.csv 2>/dev/null
