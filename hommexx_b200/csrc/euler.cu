@@ -307,6 +307,11 @@ __global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HV == 2 ? HXX
     }
     plane_store(f, r);
   }
+  // the limiter's weight sum does not depend on the tracer (serial order k = 0..15, as the reference)
+  double sumc = c[0];
+  HXX_UNROLL
+  for (int p = 1; p < NPSQ; ++p) sumc += c[p];
+  const bool skip = sumc <= 0;
   const double dp0k = dc.dp0[k];
   const double bfac = -a.rhs_viss * a.dt * a.nu_q;
   const double alpha = -a.dt;
@@ -319,28 +324,29 @@ __global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HV == 2 ? HXX
     const double qmin0 = s_l[o], qmax0 = s_l[o + TPB];
     double qa[4] = {0.0, 0.0, 0.0, 0.0};
     if (TAVG) { qa[0] = s_a[o]; qa[1] = s_a[o + TPB]; qa[2] = s_a[o + 2 * TPB]; qa[3] = s_a[o + 3 * TPB]; }
+    // The qdp plane becomes the advected value in place, one point at a time: with the limiter's
+    // weights that makes four live planes (c, x, gv0, gv1) at the widest spot.
     double x[NPSQ];
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) x[p] = s_q[o + p * TPB];
     {
-      double qd[NPSQ], gv0[NPSQ], gv1[NPSQ];
-      HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) qd[p] = s_q[o + p * TPB];
       // divergence_sphere_update, SphereOperators.hpp:398-444
+      double gv0[NPSQ], gv1[NPSQ];
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) {
-        const double u = s_vs0[p * TPB] * qd[p];
-        const double v = s_vs1[p * TPB] * qd[p];
+        const double u = s_vs0[p * TPB] * x[p];
+        const double v = s_vs1[p * TPB] * x[p];
         const double md = geo_ld(g, p, G_METDET);
         gv0[p] = (geo_ld(g, p, G_DINV00) * u + geo_ld(g, p, G_DINV10) * v) * md;
         gv1[p] = (geo_ld(g, p, G_DINV01) * u + geo_ld(g, p, G_DINV11) * v) * md;
       }
-      double dx[NPSQ], dy[NPSQ];
-      deriv_pair(gv0, gv1, dx, dy);
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) x[p] = qd[p] + alpha * ((dx[p] + dy[p]) * geo_ld(g, p, G_RMETDET_R));
-    }
-    if (HV == 2) {  // the prepared hyperviscosity term
-      HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) x[p] += s_b[o + p * TPB];
+      for (int p = 0; p < NPSQ; ++p) {
+        double dx, dy;
+        deriv_point(gv0, gv1, p / NP, p % NP, dx, dy);
+        x[p] = x[p] + alpha * ((dx + dy) * geo_ld(g, p, G_RMETDET_R));
+        if (HV == 2) x[p] += s_b[o + p * TPB];  // the prepared hyperviscosity term
+      }
     }
     if (HV == 1) {
       // x is parked in the (already consumed) qdp staging slot while the Laplacian needs registers
@@ -355,14 +361,14 @@ __global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HV == 2 ? HXX
         x[p] = s_q[o + p * TPB] + div_rcp(bfac * dp0k * lap[p], geo_ld(g, p, G_SPHEREMP), geo_ld(g, p, G_INV_SPHEREMP));
     }
     prefetch(q + ADV_NST, buf);  // the staged planes of tracer q are in registers now: refill the slot
-    // limiter shell :693-761
-    double qmin = qmin0, qmax = qmax0;
-    double xs[NPSQ];
-    HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) xs[p] = x[p] / s_dpk[p * TPB];
-    if (limiter_level(a.limiter_option, c, xs, qmin, qmax)) {
+    // limiter shell :693-761; a level whose weights do not sum to a positive number is left alone
+    if (!skip) {
+      double qmin = qmin0, qmax = qmax0;
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) x[p] = xs[p] * s_dpk[p * TPB];
+      for (int p = 0; p < NPSQ; ++p) x[p] = x[p] / s_dpk[p * TPB];
+      limiter_level_w(a.limiter_option, c, sumc, x, qmin, qmax);
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) x[p] = x[p] * s_dpk[p * TPB];
       if (qmin != qmin0) qlp[0] = qmin;
       if (qmax != qmax0) qlp[NLEV] = qmax;
     }
@@ -413,7 +419,7 @@ static int tracer_chunk() {
   static int qc = 0;
   if (!qc) {
     const char* e = std::getenv("HXX_QCHUNK");
-    qc = e ? std::max(1, std::atoi(e)) : 20;
+    qc = e ? std::max(1, std::atoi(e)) : 40;
   }
   return qc;
 }

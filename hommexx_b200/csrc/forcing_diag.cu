@@ -44,21 +44,42 @@ __global__ void tracer_forcing_ps_kernel(double* __restrict__ ps_v, const double
   ps_v[((size_t)ie * NTL + np1) * NPSQ + p] += acc;
 }
 
-// tracer_forcing :110-146: qdp += clamped dt FQ, then Q = qdp / dp(ps_v)
-__global__ void tracer_forcing_kernel(double* __restrict__ qdp, double* __restrict__ Q, const double* __restrict__ fq,
-                                      const double* __restrict__ ps_v, int np1, int np1_qdp, double dt) {
-  const int ie = blockIdx.x, q = blockIdx.y;
-  double* qd = qdp + off_q(ie, np1_qdp, q);
-  double* out = Q + ((size_t)ie * QSIZE_D + q) * NLF;
-  const double* f = fq + ((size_t)ie * QSIZE_D + q) * NLF;
-  const double* ps = ps_v + ((size_t)ie * NTL + np1) * NPSQ;
-  for (int i = threadIdx.x; i < NLF; i += blockDim.x) {
-    const int p = i / NLEV, k = i % NLEV;
-    const double qs = qd[i];
-    const double r = qs + clamped_increment(qs, dt * f[i]);
-    qd[i] = r;
-    const double dp = dc.dai[k] * dc.ps0 + dc.dbi[k] * ps[p];
-    out[i] = r / dp;
+// tracer_forcing :110-146: qdp += clamped dt FQ, then Q = qdp / dp(ps_v). One thread per (element,
+// point, level) walks the tracers four at a time (16 independent 8-byte requests in flight); the layer
+// thickness and its reciprocal are computed once per thread, the quotient is div_rcp's.
+__global__ void __launch_bounds__(256) tracer_forcing_kernel(double* __restrict__ qdp, double* __restrict__ Q,
+                                                             const double* __restrict__ fq,
+                                                             const double* __restrict__ ps_v, int nelem, int qsize,
+                                                             int np1, int np1_qdp, double dt) {
+  const long long gidx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (gidx >= (long long)nelem * NLF) return;
+  const int ie = (int)(gidx / NLF), i = (int)(gidx % NLF);
+  const int p = i / NLEV, k = i % NLEV;
+  const double dp = dc.dai[k] * dc.ps0 + dc.dbi[k] * ps_v[((size_t)ie * NTL + np1) * NPSQ + p];
+  const double rdp = 1.0 / dp;
+  double* qd = qdp + off_q(ie, np1_qdp, 0) + i;
+  double* out = Q + (size_t)ie * QSIZE_D * NLF + i;
+  const double* f = fq + (size_t)ie * QSIZE_D * NLF + i;
+  int q = 0;
+  for (; q + 4 <= qsize; q += 4) {
+    double qs[4], fv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      qs[j] = qd[(size_t)(q + j) * NLF];
+      fv[j] = f[(size_t)(q + j) * NLF];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double r = qs[j] + clamped_increment(qs[j], dt * fv[j]);
+      qd[(size_t)(q + j) * NLF] = r;
+      out[(size_t)(q + j) * NLF] = div_rcp(r, dp, rdp);
+    }
+  }
+  for (; q < qsize; ++q) {
+    const double qs = qd[(size_t)q * NLF];
+    const double r = qs + clamped_increment(qs, dt * f[(size_t)q * NLF]);
+    qd[(size_t)q * NLF] = r;
+    out[(size_t)q * NLF] = div_rcp(r, dp, rdp);
   }
 }
 
@@ -85,7 +106,9 @@ void apply_cam_forcing(double dt, bool tracers) {
   }
   if (S.p.qsize > 0) {
     PROBE(K_FORCING);
-    tracer_forcing_kernel<<<dim3(S.nelemd, S.p.qsize), 288, 0, S.stream>>>(S.qdp, S.Q, S.fq, S.ps_v, S.n0, S.n0_qdp, dt);
+    const long long nthr = (long long)S.nelemd * NLF;
+    tracer_forcing_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, S.stream>>>(S.qdp, S.Q, S.fq, S.ps_v, S.nelemd,
+                                                                             S.p.qsize, S.n0, S.n0_qdp, dt);
     KERNEL_LAUNCHED(K_FORCING);
   }
 }

@@ -9,15 +9,13 @@ namespace hxx {
 // x = ptens/dpmass, c = spheremp*dpmass (both prepared by the caller). minp/maxp are the
 // level's qlim entries and are updated as the reference updates them. Returns false when the
 // level is skipped (sum of weights <= 0), in which case x must not be written back.
-__device__ __forceinline__ bool limiter_level(int limiter_option, const double (&c)[NPSQ], double (&x)[NPSQ],
-                                              double& qmin, double& qmax) {
-  double mass = x[0] * c[0], sumc = c[0];
+// limiter_level_w: the same with the weight sum sumc = c[0] + ... + c[15] (> 0) supplied by the caller,
+// who computes it once for all tracers of a level.
+__device__ __forceinline__ void limiter_level_w(int limiter_option, const double (&c)[NPSQ], double sumc,
+                                                double (&x)[NPSQ], double& qmin, double& qmax) {
+  double mass = x[0] * c[0];
 #pragma unroll
-  for (int k = 1; k < NPSQ; ++k) {
-    mass += x[k] * c[k];
-    sumc += c[k];
-  }
-  if (sumc <= 0) return false;
+  for (int k = 1; k < NPSQ; ++k) mass += x[k] * c[k];
   double minp = qmin, maxp = qmax;
   if (minp < 0) minp = qmin = 0.0;
   if (mass < minp * sumc) minp = qmin = mass / sumc;
@@ -83,6 +81,15 @@ __device__ __forceinline__ bool limiter_level(int limiter_option, const double (
       }
     }
   }
+}
+
+__device__ __forceinline__ bool limiter_level(int limiter_option, const double (&c)[NPSQ], double (&x)[NPSQ],
+                                              double& qmin, double& qmax) {
+  double sumc = c[0];
+#pragma unroll
+  for (int k = 1; k < NPSQ; ++k) sumc += c[k];
+  if (sumc <= 0) return false;
+  limiter_level_w(limiter_option, c, sumc, x, qmin, qmax);
   return true;
 }
 
