@@ -145,36 +145,27 @@ __global__ void __launch_bounds__(TPB, BIH ? 2 : 4) euler_qminmax_kernel(const E
   cp_async_wait<0>();
 }
 
-// shared-memory doubles per thread: vstar (2x16), dpdissk (16), 2 staged qdp planes (2x16) and,
-// on the hyperviscosity stage, 2 staged qtens_biharmonic planes (2x16); slot s of thread t lives
-// at [s][t], so a warp's access to one slot is 256 contiguous bytes (conflict-free).
-#ifndef HXX_ADV_STAGES
-#define HXX_ADV_STAGES 1
-#endif
+// Advection kernel, per-thread storage. Shared-memory slots (slot s of thread t lives at [s][t], so a
+// warp's access to one slot is 256 contiguous bytes): vstar (2x16), dpdissk (16) and its reciprocal
+// (16), plus, on the hyperviscosity stage, one staged plane of the prepared term (16, cp.async).
+// Registers: the limiter weights c (16), the tracer plane being advected (16) and the NEXT tracer's
+// plane (16), whose loads are issued before the limiter starts and land while it runs.
+// two blocks per SM: at three the register cap (168) forces spills that cost more than the extra warps give
 #ifndef HXX_ADV_MINB
-#define HXX_ADV_MINB 3
+#define HXX_ADV_MINB 2
 #endif
 #ifndef HXX_ADV_MINB_HV
 #define HXX_ADV_MINB_HV 2
 #endif
-constexpr int ADV_NST = HXX_ADV_STAGES;  // staged tracers in flight per thread
-// HV mode of the advection kernel: 0 = no hyperviscosity term; 1 = second Laplacian applied on
-// the fly (one pass less over qtens_biharmonic, but the heaviest register footprint); 2 = the term
-// was prepared in place by euler_hvpost_kernel and is only added here.
-// shared-memory slots per thread: vstar (2x16) and dpdissk (16), then per staged tracer the qdp
-// plane (16), the qtens_biharmonic / prepared-term plane when HV != 0 (16), the two qlim rows and
-// the four interior time-average partners when TAVG
-template <int HV, bool TAVG>
-__host__ __device__ constexpr int advect_stage_slots() { return NPSQ + (HV ? NPSQ : 0) + 2 + (TAVG ? 4 : 0); }
-template <int HV, bool TAVG>
-__host__ __device__ constexpr int advect_slots() { return 48 + ADV_NST * advect_stage_slots<HV, TAVG>(); }
-#ifndef HXX_ADV_MINB_HV2
-#define HXX_ADV_MINB_HV2 2
-#endif
+template <bool HV>
+__host__ __device__ constexpr int advect_slots() { return 64 + (HV ? NPSQ : 0); }
 
 // compute_biharmonic_post :216-231 with rhsviss_adjustment :293-310, in place:
 // qtens_biharmonic <- (-rhs_viss dt nu_q) dp0 laplace(qtens_biharmonic) / spheremp
-__global__ void __launch_bounds__(TPB, 3) euler_hvpost_kernel(const EulerArgs a) {
+#ifndef HXX_HVPOST_MINB
+#define HXX_HVPOST_MINB 2
+#endif
+__global__ void __launch_bounds__(TPB, HXX_HVPOST_MINB) euler_hvpost_kernel(const EulerArgs a) {
   extern __shared__ double s_all[];
   __shared__ double s_geo[geo_span(TPB) * NPSQ * GEO_N];
   const int e_first = (int)(((long long)blockIdx.x * TPB) / NLEV);
@@ -214,11 +205,10 @@ __global__ void __launch_bounds__(TPB, 3) euler_hvpost_kernel(const EulerArgs a)
   cp_async_wait<0>();
 }
 
-// advect_and_limit :317-332 = compute_2d_advection_step (:585-626) + run_tracer_phase (:571-582),
-// with compute_biharmonic_post (:216-231, rhsviss_adjustment :293-310) applied on the fly.
-template <int HV, bool TAVG>
-__global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HV == 2 ? HXX_ADV_MINB_HV2 : HXX_ADV_MINB)
-    euler_advect_kernel(const EulerArgs a) {
+// advect_and_limit :317-332 = compute_2d_advection_step (:585-626) + run_tracer_phase (:571-582).
+// HV: the hyperviscosity term prepared in place by euler_hvpost_kernel is added (:216-231).
+template <bool HV, bool TAVG>
+__global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) euler_advect_kernel(const EulerArgs a) {
   extern __shared__ double s_all[];
   __shared__ double s_geo[geo_span(TPB) * NPSQ * GEO_N];
   const int e_first = (int)(((long long)blockIdx.x * TPB) / NLEV);
@@ -229,45 +219,40 @@ __global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HV == 2 ? HXX
   double* const s_vs0 = s_all + tid;
   double* const s_vs1 = s_all + 16 * TPB + tid;
   double* const s_dpk = s_all + 32 * TPB + tid;
-  constexpr int SS = advect_stage_slots<HV, TAVG>();
-  double* const s_q = s_all + 48 * TPB + tid;               // stage i: slots [i*SS, (i+1)*SS)
-  double* const s_b = s_q + NPSQ * TPB;                     // second plane (HV != 0)
-  double* const s_l = s_q + (HV ? 2 : 1) * NPSQ * TPB;      // qlim rows
-  double* const s_a = s_l + 2 * TPB;                        // time-average partners (TAVG)
+  double* const s_rdpk = s_all + 48 * TPB + tid;
+  double* const s_b = s_all + 64 * TPB + tid;  // HV: the prepared term of the tracer in flight
   const GeoShared g{s_geo + (ie - e_first) * NPSQ * GEO_N};
-  const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
   const int q0 = blockIdx.y * a.qchunk, q1 = min(a.qsize, q0 + a.qchunk);
   const double* const qin = a.qdp + off_q(ie, a.n0_qdp, 0) + k;
   const double* const qtb = a.qtens_biharmonic + (size_t)ie * QSIZE_D * NLF + k;
   const double* const qlim_in = a.qlim + (size_t)ie * QSIZE_D * 2 * NLEV + k;
   const double* const qavg = TAVG ? a.qdp + off_q(ie, a.tavg_n0, 0) + k : nullptr;
-  auto prefetch = [&](int q, int buf) {
-    if (q < q1) {
-      const int o = buf * SS * TPB;
-      const double* src = qin + (size_t)q * NLF;
-      HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) cp_async8(s_q + o + p * TPB, src + p * NLEV);
-      if (HV) {
+  auto stage_b = [&](int q) {
+    if (HV) {
+      if (q < q1) {
         const double* sb = qtb + (size_t)q * NLF;
         HXX_UNROLL
-        for (int p = 0; p < NPSQ; ++p) cp_async8(s_b + o + p * TPB, sb + p * NLEV);
+        for (int p = 0; p < NPSQ; ++p) cp_async8(s_b + p * TPB, sb + p * NLEV);
       }
-      cp_async8(s_l + o, qlim_in + (size_t)q * 2 * NLEV);
-      cp_async8(s_l + o + TPB, qlim_in + (size_t)q * 2 * NLEV + NLEV);
-      if (TAVG) {  // qdp_time_avg :379-403 partner values of the 4 interior points
+      cp_async_commit();
+    }
+  };
+  // next tracer's plane, qlim rows and time-average partners (qdp_time_avg :379-403, interior points)
+  double xn[NPSQ], qmin_n = 0.0, qmax_n = 0.0, qa_n[4] = {0.0, 0.0, 0.0, 0.0};
+  auto load_next = [&](int q) {
+    if (q < q1) {
+      plane_load(qin + (size_t)q * NLF, xn);
+      qmin_n = qlim_in[(size_t)q * 2 * NLEV];
+      qmax_n = qlim_in[(size_t)q * 2 * NLEV + NLEV];
+      if (TAVG) {
         const double* pa = qavg + (size_t)q * NLF;
-        cp_async8(s_a + o, pa + 5 * NLEV);
-        cp_async8(s_a + o + TPB, pa + 6 * NLEV);
-        cp_async8(s_a + o + 2 * TPB, pa + 9 * NLEV);
-        cp_async8(s_a + o + 3 * TPB, pa + 10 * NLEV);
+        qa_n[0] = pa[5 * NLEV]; qa_n[1] = pa[6 * NLEV]; qa_n[2] = pa[9 * NLEV]; qa_n[3] = pa[10 * NLEV];
       }
     }
-    cp_async_commit();  // possibly empty: keeps one group per loop iteration
   };
-  HXX_UNROLL
-  for (int i = 0; i < ADV_NST; ++i) prefetch(q0 + i, i);
+  stage_b(q0);
 
-  const bool add_ps_diss = a.nu_p > 0 && HV != 0;
+  const bool add_ps_diss = a.nu_p > 0 && HV;
   const double diss_fac = add_ps_diss ? -a.rhs_viss * a.dt * a.nu_q : 0.0;
   double c[NPSQ];
   {
@@ -277,25 +262,39 @@ __global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HV == 2 ? HXX
     const double* n0 = a.derived_vn0 + ((size_t)ie * 2 + 0) * NLF + k;
     const double* n1 = a.derived_vn0 + ((size_t)ie * 2 + 1) * NLF + k;
     const double* db = a.dpdiss_biharmonic + off_f(ie) + k;
-    double r0[NPSQ], r1[NPSQ], r2[NPSQ], r3[NPSQ], r4[NPSQ], r5[NPSQ];
-    plane_load(dd, r0);
-    plane_load(dj, r1);
-    plane_load(dv, r2);
-    plane_load(n0, r3);
-    plane_load(n1, r4);
-    if (add_ps_diss) plane_load(db, r5);
-    HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) {
-      const double sm_ = geo_ld(g, p, G_SPHEREMP);
-      const double dp = r0[p] - a.rhsmdt * r1[p];
-      s_vs0[p * TPB] = r3[p] / dp;
-      s_vs1[p * TPB] = r4[p] / dp;
-      double d = dp - a.dt * r2[p];
-      if (add_ps_diss) d += diss_fac * r5[p] / sm_;
-      s_dpk[p * TPB] = d;
-      c[p] = sm_ * d;
+    // two rounds of loads, so that no more than four planes are in registers at once
+    double dp[NPSQ];
+    {
+      double r0[NPSQ], r1[NPSQ], r3[NPSQ], r4[NPSQ];
+      plane_load(dd, r0);
+      plane_load(dj, r1);
+      plane_load(n0, r3);
+      plane_load(n1, r4);
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) {
+        dp[p] = r0[p] - a.rhsmdt * r1[p];
+        const double rdp = 1.0 / dp[p];
+        s_vs0[p * TPB] = div_rcp(r3[p], dp[p], rdp);
+        s_vs1[p * TPB] = div_rcp(r4[p], dp[p], rdp);
+      }
+    }
+    phase_fence();
+    {
+      double r2[NPSQ], r5[NPSQ];
+      plane_load(dv, r2);
+      if (add_ps_diss) plane_load(db, r5);
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) {
+        const double sm_ = geo_ld(g, p, G_SPHEREMP);
+        double d = dp[p] - a.dt * r2[p];
+        if (add_ps_diss) d += div_rcp(diss_fac * r5[p], sm_, geo_ld(g, p, G_INV_SPHEREMP));
+        s_dpk[p * TPB] = d;
+        s_rdpk[p * TPB] = 1.0 / d;
+        c[p] = sm_ * d;
+      }
     }
   }
+  phase_fence();
   if (blockIdx.y == 0 && a.f_dss) {  // f_dss *= spheremp (and the interior part of the DSS rspheremp)
     double* f = a.f_dss + off_f(ie) + k;
     double r[NPSQ];
@@ -312,23 +311,18 @@ __global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HV == 2 ? HXX
   HXX_UNROLL
   for (int p = 1; p < NPSQ; ++p) sumc += c[p];
   const bool skip = sumc <= 0;
-  const double dp0k = dc.dp0[k];
-  const double bfac = -a.rhs_viss * a.dt * a.nu_q;
   const double alpha = -a.dt;
   double* qlp = a.qlim + ((size_t)ie * QSIZE_D + q0) * 2 * NLEV + k;
   double* out = a.qdp + off_q(ie, a.np1_qdp, q0) + k;
+  load_next(q0);
   for (int q = q0; q < q1; ++q, qlp += 2 * NLEV, out += NLF) {
-    const int buf = (q - q0) % ADV_NST;
-    const int o = buf * SS * TPB;
-    cp_async_wait<ADV_NST - 1>();  // this thread's copies of tracer q have landed
-    const double qmin0 = s_l[o], qmax0 = s_l[o + TPB];
-    double qa[4] = {0.0, 0.0, 0.0, 0.0};
-    if (TAVG) { qa[0] = s_a[o]; qa[1] = s_a[o + TPB]; qa[2] = s_a[o + 2 * TPB]; qa[3] = s_a[o + 3 * TPB]; }
+    const double qmin0 = qmin_n, qmax0 = qmax_n;
+    const double qa[4] = {qa_n[0], qa_n[1], qa_n[2], qa_n[3]};
     // The qdp plane becomes the advected value in place, one point at a time: with the limiter's
     // weights that makes four live planes (c, x, gv0, gv1) at the widest spot.
     double x[NPSQ];
     HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) x[p] = s_q[o + p * TPB];
+    for (int p = 0; p < NPSQ; ++p) x[p] = xn[p];
     {
       // divergence_sphere_update, SphereOperators.hpp:398-444
       double gv0[NPSQ], gv1[NPSQ];
@@ -340,32 +334,25 @@ __global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HV == 2 ? HXX
         gv0[p] = (geo_ld(g, p, G_DINV00) * u + geo_ld(g, p, G_DINV10) * v) * md;
         gv1[p] = (geo_ld(g, p, G_DINV01) * u + geo_ld(g, p, G_DINV11) * v) * md;
       }
+      if (HV) cp_async_wait<0>();  // this thread's copy of the prepared term has landed
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) {
         double dx, dy;
         deriv_point(gv0, gv1, p / NP, p % NP, dx, dy);
         x[p] = x[p] + alpha * ((dx + dy) * geo_ld(g, p, G_RMETDET_R));
-        if (HV == 2) x[p] += s_b[o + p * TPB];  // the prepared hyperviscosity term
+        if (HV) x[p] += s_b[p * TPB];
       }
     }
-    if (HV == 1) {
-      // x is parked in the (already consumed) qdp staging slot while the Laplacian needs registers
-      HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) s_q[o + p * TPB] = x[p];
-      double s[NPSQ], lap[NPSQ];
-      HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) s[p] = s_b[o + p * TPB];
-      if (a.consthv) laplace_simple(g, s, lap); else laplace_tensor(g, tv, s, lap);
-      HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p)
-        x[p] = s_q[o + p * TPB] + div_rcp(bfac * dp0k * lap[p], geo_ld(g, p, G_SPHEREMP), geo_ld(g, p, G_INV_SPHEREMP));
-    }
-    prefetch(q + ADV_NST, buf);  // the staged planes of tracer q are in registers now: refill the slot
+    // the next tracer's loads go out now and land while the limiter runs
+    phase_fence();
+    stage_b(q + 1);
+    load_next(q + 1);
+    phase_fence();
     // limiter shell :693-761; a level whose weights do not sum to a positive number is left alone
     if (!skip) {
       double qmin = qmin0, qmax = qmax0;
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) x[p] = x[p] / s_dpk[p * TPB];
+      for (int p = 0; p < NPSQ; ++p) x[p] = div_rcp(x[p], s_dpk[p * TPB], s_rdpk[p * TPB]);
       limiter_level_w(a.limiter_option, c, sumc, x, qmin, qmax);
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) x[p] = x[p] * s_dpk[p * TPB];
@@ -382,7 +369,7 @@ __global__ void __launch_bounds__(TPB, HV == 1 ? HXX_ADV_MINB_HV : HV == 2 ? HXX
       out[p * NLEV] = r;
     }
   }
-  cp_async_wait<0>();
+  if (HV) cp_async_wait<0>();
 }
 
 // f_dss *= spheremp on its own, for the one case where the advection kernel still reads it
@@ -456,30 +443,19 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
     minmax_exchange();
   }
   a.qlim = S.qlim;  // minmax_exchange swaps the double buffer
-  static int hv_split = -1;
-  if (hv_split < 0) {
-    const char* e = std::getenv("HXX_HV_SPLIT");
-    hv_split = e ? std::atoi(e) : 1;
-  }
-  const int hv = S.rhs_viss == 0.0 ? 0 : hv_split ? 2 : 1;
+  const bool hv = S.rhs_viss != 0.0;
   const bool tavg = tavg_n0_qdp >= 0;
-  auto slots = [&]() {
-    return hv == 1 ? (tavg ? advect_slots<1, true>() : advect_slots<1, false>())
-         : hv == 2 ? (tavg ? advect_slots<2, true>() : advect_slots<2, false>())
-                   : (tavg ? advect_slots<0, true>() : advect_slots<0, false>());
-  };
-  const size_t smem = (size_t)slots() * TPB * sizeof(double);
+  const size_t smem = (size_t)(hv ? advect_slots<true>() : advect_slots<false>()) * TPB * sizeof(double);
   static bool attr = false;
   if (!attr) {
 #define HXX_ADV_ATTR(H, T)                                                                                  \
   CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                               advect_slots<H, T>() * TPB * (int)sizeof(double)))
-    HXX_ADV_ATTR(0, false); HXX_ADV_ATTR(0, true); HXX_ADV_ATTR(1, false); HXX_ADV_ATTR(1, true);
-    HXX_ADV_ATTR(2, false); HXX_ADV_ATTR(2, true);
+                               advect_slots<H>() * TPB * (int)sizeof(double)))
+    HXX_ADV_ATTR(false, false); HXX_ADV_ATTR(false, true); HXX_ADV_ATTR(true, false); HXX_ADV_ATTR(true, true);
 #undef HXX_ADV_ATTR
     attr = true;
   }
-  if (hv == 2) {
+  if (hv) {  // compute_biharmonic_post: the second Laplacian, in place
     PROBE(K_EULER_QMINMAX);
     euler_hvpost_kernel<<<grid, TPB, 2 * (size_t)NPSQ * TPB * sizeof(double), S.stream>>>(a);
     KERNEL_LAUNCHED(K_EULER_QMINMAX);
@@ -490,12 +466,10 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   const bool separate = (fdss == S.divdp_proj && a.rhsmdt != 0.0);
   if (separate) a.f_dss = nullptr;
   PROBE(K_EULER_ADVECT);
-  if (hv == 1 && tavg) euler_advect_kernel<1, true><<<grid, TPB, smem, S.stream>>>(a);
-  else if (hv == 1) euler_advect_kernel<1, false><<<grid, TPB, smem, S.stream>>>(a);
-  else if (hv == 2 && tavg) euler_advect_kernel<2, true><<<grid, TPB, smem, S.stream>>>(a);
-  else if (hv == 2) euler_advect_kernel<2, false><<<grid, TPB, smem, S.stream>>>(a);
-  else if (tavg) euler_advect_kernel<0, true><<<grid, TPB, smem, S.stream>>>(a);
-  else euler_advect_kernel<0, false><<<grid, TPB, smem, S.stream>>>(a);
+  if (hv && tavg) euler_advect_kernel<true, true><<<grid, TPB, smem, S.stream>>>(a);
+  else if (hv) euler_advect_kernel<true, false><<<grid, TPB, smem, S.stream>>>(a);
+  else if (tavg) euler_advect_kernel<false, true><<<grid, TPB, smem, S.stream>>>(a);
+  else euler_advect_kernel<false, false><<<grid, TPB, smem, S.stream>>>(a);
   KERNEL_LAUNCHED(K_EULER_ADVECT);
   if (separate) {
     PROBE(K_EULER_FDSS);
