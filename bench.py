@@ -37,6 +37,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Native libraries (NCCL's version banner, NCCL_DEBUG output) write to file descriptor 1. The contract is
+# ONE JSON line on stdout, so fd 1 is pointed at stderr for the whole run and the line goes to the
+# saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -103,6 +114,11 @@ def workload(args, n_gpus):
     else:
         ne = int(round((900.0 * n_gpus) ** 0.5))
     over = dict(ne=ne, npart=n_gpus)
+    if ne != 30:
+        # the namelist's time step and hyperviscosity are tuned to ne30; other meshes follow HOMME's
+        # usual scaling (tstep ~ 1/ne, nu ~ dx^3.2: homme-ne120-v1.nl has tstep 75, nu 1e13)
+        nu = 1e15 * (30.0 / ne) ** 3.2
+        over.update(tstep=300.0 * 30.0 / ne, nu=nu, nu_p=nu, nu_q=nu, nu_s=nu)
     if args.qsize:
         over.update(qsize=args.qsize)
     return homme.preset("ne30", **over)
@@ -166,7 +182,7 @@ def run_reference(args):
            "cpu_baseline": {"value": val, "unit": "element-steps/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "element-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def pin_driver_arrays(h, torch):
@@ -378,7 +394,7 @@ def main():
                "step_roofline": {"algorithmic_bytes_per_element_step": step_bytes, "achieved_gbs_per_gpu": step_gbs,
                                  "frac": step_gbs / peak, "peak": peak},
                "e2e": e2e, "cpu_baseline": cpu, "breakdown": breakdown}
-        print(json.dumps(out), flush=True)
+        emit(out)
     h.close()
     if dist is not None:
         dist.barrier()

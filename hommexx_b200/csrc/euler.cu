@@ -163,7 +163,7 @@ __host__ __device__ constexpr int advect_slots() { return 64 + (HV ? NPSQ : 0); 
 // compute_biharmonic_post :216-231 with rhsviss_adjustment :293-310, in place:
 // qtens_biharmonic <- (-rhs_viss dt nu_q) dp0 laplace(qtens_biharmonic) / spheremp
 #ifndef HXX_HVPOST_MINB
-#define HXX_HVPOST_MINB 2
+#define HXX_HVPOST_MINB 3
 #endif
 __global__ void __launch_bounds__(TPB, HXX_HVPOST_MINB) euler_hvpost_kernel(const EulerArgs a) {
   extern __shared__ double s_all[];
@@ -456,6 +456,12 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
     attr = true;
   }
   if (hv) {  // compute_biharmonic_post: the second Laplacian, in place
+    static bool attr_hp = false;
+    if (!attr_hp) {
+      CUDA_OK(cudaFuncSetAttribute(euler_hvpost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   2 * NPSQ * TPB * (int)sizeof(double)));
+      attr_hp = true;
+    }
     PROBE(K_EULER_QMINMAX);
     euler_hvpost_kernel<<<grid, TPB, 2 * (size_t)NPSQ * TPB * sizeof(double), S.stream>>>(a);
     KERNEL_LAUNCHED(K_EULER_QMINMAX);

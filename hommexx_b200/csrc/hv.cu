@@ -13,6 +13,9 @@ HXX_DEFINE_CONSTANTS()
 
 namespace hxx {
 
+#ifndef HXX_HV_MINB
+#define HXX_HV_MINB 2
+#endif
 struct HvArgs {
   const double *geo, *metinv, *tensorvisc, *vec_sph2cart;
   double *v, *t, *dp3d, *vtens, *ttens, *dptens, *dpdiss_ave, *dpdiss_biharmonic;
@@ -30,40 +33,66 @@ __device__ __forceinline__ bool map_thread(int nelem, int& ie, int& k) {
   return ie < nelem;
 }
 
-// biharmonic_wk_dp3d first pass; interior points already carry the rspheremp of the DSS that follows
-__global__ void __launch_bounds__(TPB, 2) hv_first_laplace_kernel(const HvArgs a) {
-  int ie, k;
-  if (!map_thread(a.nelem, ie, k)) return;
-  const double* __restrict__ g = a.geo + (size_t)ie * NPSQ * GEO_N;
-  const double* __restrict__ mi = a.metinv + (size_t)ie * 4 * NPSQ;
-  double s[NPSQ], lap[NPSQ];
-  plane_load(a.t + off_s(ie, a.np1) + k, s);
-  laplace_simple(g, s, lap);
-  HXX_UNROLL
-  for (int p = 0; p < NPSQ; ++p)
-    if (is_interior_pt(p)) lap[p] *= geo_ld(g, p, G_RSPHEREMP);
-  plane_store(a.ttens + off_f(ie) + k, lap);
-  plane_load(a.dp3d + off_s(ie, a.np1) + k, s);
-  laplace_simple(g, s, lap);
-  HXX_UNROLL
-  for (int p = 0; p < NPSQ; ++p)
-    if (is_interior_pt(p)) lap[p] *= geo_ld(g, p, G_RSPHEREMP);
-  plane_store(a.dptens + off_f(ie) + k, lap);
-  double l1[NPSQ];
-  vlaplace_sphere_wk_contra_mem(g, mi, a.nu_ratio1, a.v + off_v(ie, a.np1, 0) + k, a.v + off_v(ie, a.np1, 1) + k, lap, l1);
-  HXX_UNROLL
-  for (int p = 0; p < NPSQ; ++p)
-    if (is_interior_pt(p)) {
-      const double rs = geo_ld(g, p, G_RSPHEREMP);
-      lap[p] *= rs;
-      l1[p] *= rs;
-    }
-  plane_store(a.vtens + ((size_t)ie * 2 + 0) * NLF + k, lap);
-  plane_store(a.vtens + ((size_t)ie * 2 + 1) * NLF + k, l1);
+// Cooperative copy of a per-element [N]-double record (metinv: 64) for the elements a block touches.
+template <int NE, int N, int NT>
+__device__ __forceinline__ void stage_records(double* s_dst, const double* __restrict__ src, int e_first, int nelem) {
+  for (int i = threadIdx.x; i < NE * N; i += NT) {
+    const int e = e_first + i / N;
+    if (e < nelem) s_dst[i] = __ldg(src + (size_t)e_first * N + i);
+  }
 }
 
-// second Laplacian + TagHyperPreExchange. Two decisions keep the register footprint (and with
-// it the occupancy) in check: the scalar fields (T, dp3d) and the vector field are separate
+// All three kernels below finish their operators one point at a time (hxx_sphere.cuh): a result goes to
+// HBM as soon as it exists, every plane a kernel reads is in registers before its first store, and the
+// weak gradient inside the vector Laplacian waits in per-thread shared-memory slots [32][TPB].
+
+// biharmonic_wk_dp3d first pass; interior points already carry the rspheremp of the DSS that follows
+__global__ void __launch_bounds__(TPB, HXX_HV_MINB) hv_first_laplace_kernel(const HvArgs a) {
+  extern __shared__ double s_park[];
+  __shared__ double s_geo[geo_span(TPB) * NPSQ * GEO_N];
+  __shared__ double s_mi[geo_span(TPB) * 4 * NPSQ];
+  const int e_first = (int)(((long long)blockIdx.x * TPB) / NLEV);
+  stage_records<geo_span(TPB), 4 * NPSQ, TPB>(s_mi, a.metinv, e_first, a.nelem);
+  stage_geo<geo_span(TPB), TPB>(s_geo, a.geo, e_first, a.nelem);
+  int ie, k;
+  if (!map_thread(a.nelem, ie, k)) return;
+  const GeoShared g{s_geo + (ie - e_first) * NPSQ * GEO_N};
+  const GeoShared mi{s_mi + (ie - e_first) * 4 * NPSQ};
+  {
+    double s[NPSQ];
+    plane_load(a.t + off_s(ie, a.np1) + k, s);
+    double* out = a.ttens + off_f(ie) + k;
+    laplace_points<false>(g, nullptr, s, [&](int p, double lap) {
+      if (is_interior_pt(p)) lap *= geo_ld(g, p, G_RSPHEREMP);
+      out[p * NLEV] = lap;
+    });
+  }
+  phase_fence();
+  {
+    double s[NPSQ];
+    plane_load(a.dp3d + off_s(ie, a.np1) + k, s);
+    double* out = a.dptens + off_f(ie) + k;
+    laplace_points<false>(g, nullptr, s, [&](int p, double lap) {
+      if (is_interior_pt(p)) lap *= geo_ld(g, p, G_RSPHEREMP);
+      out[p * NLEV] = lap;
+    });
+  }
+  phase_fence();
+  double* o0 = a.vtens + ((size_t)ie * 2 + 0) * NLF + k;
+  double* o1 = a.vtens + ((size_t)ie * 2 + 1) * NLF + k;
+  vlaplace_contra_points(g, mi, a.nu_ratio1, a.v + off_v(ie, a.np1, 0) + k, a.v + off_v(ie, a.np1, 1) + k,
+                         s_park + threadIdx.x, s_park + NPSQ * TPB + threadIdx.x, TPB, [&](int p, double l0, double l1) {
+                           if (is_interior_pt(p)) {
+                             const double rs = geo_ld(g, p, G_RSPHEREMP);
+                             l0 *= rs;
+                             l1 *= rs;
+                           }
+                           o0[p * NLEV] = l0;
+                           o1[p * NLEV] = l1;
+                         });
+}
+
+// second Laplacian + TagHyperPreExchange. The scalar fields (T, dp3d) and the vector field are separate
 // kernels, and the nu_top sponge layer — extra Laplacians of the state on levels 0..2 only
 // (NUM_BIHARMONIC_LEV) — is a template flag: the SPONGE=true instantiation runs over just those
 // three levels of every element, the SPONGE=false one over the remaining levels, so 69 of 72
@@ -97,76 +126,98 @@ __global__ void __launch_bounds__(TPB, SPONGE ? 2 : 3) hv_second_scalar_kernel(c
   const Geo g{SPONGE ? a.geo + (size_t)ie * NPSQ * GEO_N : s_geo + (ie - e_first) * NPSQ * GEO_N};
   const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
   const double nst = (k == 0 ? 4.0 : k == 1 ? 2.0 : 1.0) * a.nu_top;  // HyperviscosityFunctorImpl.cpp:24-38
-  double s[NPSQ], lap[NPSQ], top[NPSQ];
   {  // T
     double* tt = a.ttens + off_f(ie) + k;
+    double s[NPSQ], top[SPONGE ? NPSQ : 1];
     plane_load(tt, s);
-    if (a.consthv) laplace_simple(g, s, lap); else laplace_tensor(g, tv, s, lap);
-    if (SPONGE) {
-      plane_load(a.t + off_s(ie, a.np1) + k, s);
-      laplace_simple(g, s, top);
+    if constexpr (SPONGE) {
+      double t[NPSQ];
+      plane_load(a.t + off_s(ie, a.np1) + k, t);
+      laplace_simple(g, t, top);
     }
-    HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) {
-      lap[p] *= -a.nu_s;
-      if (SPONGE) lap[p] += nst * top[p];
-    }
-    plane_store(tt, lap);
+    auto emit = [&](int p, double lap) {
+      lap *= -a.nu_s;
+      if constexpr (SPONGE) lap += nst * top[p];
+      tt[p * NLEV] = lap;
+    };
+    if (a.consthv) laplace_points<false>(g, tv, s, emit); else laplace_points<true>(g, tv, s, emit);
   }
+  phase_fence();
   {  // dp3d
     double* dt_ = a.dptens + off_f(ie) + k;
-    double dp[NPSQ];
-    plane_load(dt_, s);
-    if (a.consthv) laplace_simple(g, s, lap); else laplace_tensor(g, tv, s, lap);
+    double* dbih = a.dpdiss_biharmonic + off_f(ie) + k;
+    double dp[NPSQ], top[SPONGE ? NPSQ : 1];
     plane_load(a.dp3d + off_s(ie, a.np1) + k, dp);
+    const double hs = (double)a.hypervis_subcycle, rhs = 1.0 / hs;  // the subcycle count divides through its reciprocal
     {
-      // whole planes are loaded before the first store (a store between two loads of possibly
-      // aliasing arrays would serialise them); the subcycle count divides through its reciprocal
       double* dave = a.dpdiss_ave + off_f(ie) + k;
-      double* dbih = a.dpdiss_biharmonic + off_f(ie) + k;
-      double r0[NPSQ], r1[NPSQ];
+      double r0[NPSQ];
       plane_load(dave, r0);
-      plane_load(dbih, r1);
-      const double hs = (double)a.hypervis_subcycle, rhs = 1.0 / hs;
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) {
-        r0[p] += div_rcp(a.eta_ave_w * dp[p], hs, rhs);
-        r1[p] += div_rcp(a.eta_ave_w * lap[p], hs, rhs);
-      }
+      for (int p = 0; p < NPSQ; ++p) r0[p] += div_rcp(a.eta_ave_w * dp[p], hs, rhs);
       plane_store(dave, r0);
-      plane_store(dbih, r1);
     }
-    if (SPONGE) laplace_simple(g, dp, top);
-    HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) {
-      lap[p] *= -a.nu_p;
-      if (SPONGE) lap[p] += nst * top[p];
-      lap[p] *= a.dt;
-      lap[p] += dp[p] * geo_ld(g, p, G_SPHEREMP);
-    }
-    plane_store(dt_, lap);
+    if constexpr (SPONGE) laplace_simple(g, dp, top);
+    double s[NPSQ], r1[NPSQ];
+    plane_load(dt_, s);
+    plane_load(dbih, r1);
+    phase_fence();
+    auto emit = [&](int p, double lap) {
+      dbih[p * NLEV] = r1[p] + div_rcp(a.eta_ave_w * lap, hs, rhs);
+      lap *= -a.nu_p;
+      if constexpr (SPONGE) lap += nst * top[p];
+      lap *= a.dt;
+      lap += dp[p] * geo_ld(g, p, G_SPHEREMP);
+      dt_[p * NLEV] = lap;
+    };
+    if (a.consthv) laplace_points<false>(g, tv, s, emit); else laplace_points<true>(g, tv, s, emit);
   }
 }
 
-template <bool SPONGE>
-__global__ void __launch_bounds__(TPB, 2) hv_second_vector_kernel(const HvArgs a, int nsponge) {
-  // the main (non-sponge) instantiation walks >= NLEV - 3 levels per element, so a block spans
-  // at most HV2_SPAN elements and reads their geometry from shared memory
+template <bool SPONGE, bool CONSTHV>
+__global__ void __launch_bounds__(TPB, SPONGE ? 2 : HXX_HV_MINB) hv_second_vector_kernel(const HvArgs a, int nsponge) {
+  extern __shared__ double s_park[];
   __shared__ double s_geo[SPONGE ? 1 : HV2_SPAN * NPSQ * GEO_N];
+  __shared__ double s_mi[SPONGE ? 1 : HV2_SPAN * 4 * NPSQ];
   const int e_first = SPONGE ? 0 : (int)(((long long)blockIdx.x * TPB) / (NLEV - nsponge));
-  if (!SPONGE) stage_geo<HV2_SPAN, TPB>(s_geo, a.geo, e_first, a.nelem);
+  if (!SPONGE) {
+    stage_records<HV2_SPAN, 4 * NPSQ, TPB>(s_mi, a.metinv, e_first, a.nelem);
+    stage_geo<HV2_SPAN, TPB>(s_geo, a.geo, e_first, a.nelem);
+  }
   int ie, k;
   if (!map_thread_hv2<SPONGE>(a.nelem, nsponge, ie, k)) return;
   using Geo = typename std::conditional<SPONGE, GeoGlobal, GeoShared>::type;
   const Geo g{SPONGE ? a.geo + (size_t)ie * NPSQ * GEO_N : s_geo + (ie - e_first) * NPSQ * GEO_N};
+  const Geo mig{SPONGE ? a.metinv + (size_t)ie * 4 * NPSQ : s_mi + (ie - e_first) * 4 * NPSQ};
   const double* __restrict__ mi = a.metinv + (size_t)ie * 4 * NPSQ;
-  const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
-  const double* __restrict__ vs = a.consthv ? nullptr : a.vec_sph2cart + (size_t)ie * 6 * NPSQ;
+  const double* __restrict__ tv = CONSTHV ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
+  const double* __restrict__ vs = CONSTHV ? nullptr : a.vec_sph2cart + (size_t)ie * 6 * NPSQ;
   const double nst = (k == 0 ? 4.0 : k == 1 ? 2.0 : 1.0) * a.nu_top;
   double* vt0 = a.vtens + ((size_t)ie * 2 + 0) * NLF + k;
   double* vt1 = a.vtens + ((size_t)ie * 2 + 1) * NLF + k;
+  if constexpr (CONSTHV) {
+    double* const park0 = s_park + threadIdx.x;
+    double* const park1 = s_park + NPSQ * TPB + threadIdx.x;
+    double top0[SPONGE ? NPSQ : 1], top1[SPONGE ? NPSQ : 1];
+    if constexpr (SPONGE) {
+      vlaplace_contra_points(g, mig, 1.0, a.v + off_v(ie, a.np1, 0) + k, a.v + off_v(ie, a.np1, 1) + k, park0, park1,
+                             TPB, [&](int p, double l0, double l1) { top0[p] = l0; top1[p] = l1; });
+      phase_fence();
+    }
+    // in place: the operator's last reads of vtens are whole planes taken before its first emit
+    vlaplace_contra_points(g, mig, a.nu_ratio2, vt0, vt1, park0, park1, TPB, [&](int p, double l0, double l1) {
+      l0 *= -a.nu;
+      l1 *= -a.nu;
+      if constexpr (SPONGE) {
+        l0 += nst * top0[p];
+        l1 += nst * top1[p];
+      }
+      vt0[p * NLEV] = l0;
+      vt1[p * NLEV] = l1;
+    });
+  } else {
   double lap[NPSQ], l1[NPSQ];
-  if (a.consthv) vlaplace_sphere_wk_contra_mem(g, mi, a.nu_ratio2, vt0, vt1, lap, l1);
+  if constexpr (CONSTHV) vlaplace_sphere_wk_contra_mem(g, mi, a.nu_ratio2, vt0, vt1, lap, l1);
   else {
     double s[NPSQ], s1[NPSQ];
     plane_load(vt0, s);
@@ -189,6 +240,7 @@ __global__ void __launch_bounds__(TPB, 2) hv_second_vector_kernel(const HvArgs a
   }
   plane_store(vt0, lap);
   plane_store(vt1, l1);
+  }
 }
 
 // TagUpdateStates .hpp:134-158
@@ -224,9 +276,19 @@ void hypervis_run(int np1, double dt_in, double eta_ave_w) {
            S.dpdiss_ave, S.dpdiss_biharmonic, S.nelemd, np1, dt_in / p.hypervis_subcycle, eta_ave_w, p.nu, p.nu_s,
            p.nu_p, p.nu_top, p.nu_ratio1, p.nu_ratio2, p.hypervis_subcycle, p.consthv ? 1 : 0};
   const int nb = nblocks_flat(S.nelemd);
+  constexpr size_t park_bytes = 2 * (size_t)NPSQ * TPB * sizeof(double);  // two parked planes per thread
+  static bool attr = false;
+  if (!attr) {  // static + dynamic shared memory passes 48 KB at small NLEV (more elements per block)
+    const int pb = (int)park_bytes;
+    CUDA_OK(cudaFuncSetAttribute(hv_first_laplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
+    CUDA_OK(cudaFuncSetAttribute(hv_second_vector_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
+    CUDA_OK(cudaFuncSetAttribute(hv_second_vector_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
+    CUDA_OK(cudaFuncSetAttribute(hv_second_vector_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
+    attr = true;
+  }
   for (int icycle = 0; icycle < p.hypervis_subcycle; ++icycle) {
     PROBE(K_HV_FIRST);
-    hv_first_laplace_kernel<<<nb, TPB, 0, S.stream>>>(a);
+    hv_first_laplace_kernel<<<nb, TPB, park_bytes, S.stream>>>(a);
     KERNEL_LAUNCHED(K_HV_FIRST);
     dss_exchange(fields_hv(), true);
     {
@@ -235,9 +297,15 @@ void hypervis_run(int np1, double dt_in, double eta_ave_w) {
       const int nb_sp = (int)(((long long)S.nelemd * nsp + TPB - 1) / TPB);
       PROBE(K_HV_SECOND);
       if (nb_main) hv_second_scalar_kernel<false><<<nb_main, TPB, 0, S.stream>>>(a, nsp);
-      if (nb_main) hv_second_vector_kernel<false><<<nb_main, TPB, 0, S.stream>>>(a, nsp);
+      if (nb_main) {
+        if (p.consthv) hv_second_vector_kernel<false, true><<<nb_main, TPB, park_bytes, S.stream>>>(a, nsp);
+        else hv_second_vector_kernel<false, false><<<nb_main, TPB, park_bytes, S.stream>>>(a, nsp);
+      }
       if (nb_sp) hv_second_scalar_kernel<true><<<nb_sp, TPB, 0, S.stream>>>(a, nsp);
-      if (nb_sp) hv_second_vector_kernel<true><<<nb_sp, TPB, 0, S.stream>>>(a, nsp);
+      if (nb_sp) {
+        if (p.consthv) hv_second_vector_kernel<true, true><<<nb_sp, TPB, park_bytes, S.stream>>>(a, nsp);
+        else hv_second_vector_kernel<true, false><<<nb_sp, TPB, 0, S.stream>>>(a, nsp);
+      }
       KERNEL_LAUNCHED(K_HV_SECOND);
       S.launches += 3;
     }

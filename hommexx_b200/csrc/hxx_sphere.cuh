@@ -348,6 +348,147 @@ __device__ __forceinline__ void vlaplace_sphere_wk_cartesian(const G& g, const d
   }
 }
 
+// ---- the same operators finished one point at a time --------------------------------------------
+// emit(p, value...) is called in ascending p as soon as point p is complete, so the caller can send
+// the result to memory at once and the operator holds two work planes instead of four or five. The
+// sums and their order are those of the plane-at-a-time versions above (bit-identical results).
+
+// one point of divergence_sphere_wk's contraction (:538-583); s0, s1 = spheremp * (Dinv^T v)
+__device__ __forceinline__ double div_wk_point(const double (&s0)[NPSQ], const double (&s1)[NPSQ], int n, int m) {
+  double dd = -((s0[n * NP + 0] * dc.dvv[0][m] + s1[0 * NP + m] * dc.dvv[0][n]) * rrearth);
+  HXX_UNROLL
+  for (int j = 1; j < NP; ++j) dd -= (s0[n * NP + j] * dc.dvv[j][m] + s1[j * NP + m] * dc.dvv[j][n]) * rrearth;
+  return dd;
+}
+
+// laplace_simple (:588-597) / laplace_tensor (:604-635, tv = the element's tensorVisc [2][2][16])
+template <bool TENSOR, class G, class F>
+__device__ __forceinline__ void laplace_points(const G& g, const double* __restrict__ tv, const double (&s)[NPSQ],
+                                               F&& emit) {
+  double s0[NPSQ], s1[NPSQ];
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) {
+    double g0, g1;
+    gradient_point(g, s, p, g0, g1);
+    if (TENSOR) {
+      const double t0 = __ldg(tv + 0 * NPSQ + p) * g0 + __ldg(tv + 2 * NPSQ + p) * g1;
+      const double t1 = __ldg(tv + 1 * NPSQ + p) * g0 + __ldg(tv + 3 * NPSQ + p) * g1;
+      g0 = t0;
+      g1 = t1;
+    }
+    const double w0 = geo_ld(g, p, G_DINV00) * g0 + geo_ld(g, p, G_DINV10) * g1;
+    const double w1 = geo_ld(g, p, G_DINV01) * g0 + geo_ld(g, p, G_DINV11) * g1;
+    const double sm = geo_ld(g, p, G_SPHEREMP);
+    s0[p] = sm * w0;
+    s1[p] = sm * w1;
+  }
+  HXX_UNROLL
+  for (int p = 0; p < NPSQ; ++p) emit(p, div_wk_point(s0, s1, p / NP, p % NP));
+}
+
+// vlaplace_sphere_wk_contra (:818-862). The vector field is read from memory (level already added to
+// v0p, v1p) once per use; the weak gradient of the divergence waits in the caller's per-thread
+// shared-memory slots park0/park1 (stride `ps` doubles between points) while the curl part is built.
+// mi = the element's metinv [2][2][16]. emit(p, l0, l1).
+template <class G, class MI, class F>
+__device__ __forceinline__ void vlaplace_contra_points(const G& g, const MI& mi, double nu_ratio, const double* v0p,
+                                                       const double* v1p, double* park0, double* park1, int ps,
+                                                       F&& emit) {
+  double sc[NPSQ];
+  {  // divergence_sphere :352-392
+    double gv0[NPSQ], gv1[NPSQ];
+    {
+      double v0[NPSQ], v1[NPSQ];
+      plane_load(v0p, v0);
+      plane_load(v1p, v1);
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) {
+        const double md = geo_ld(g, p, G_METDET);
+        gv0[p] = (geo_ld(g, p, G_DINV00) * v0[p] + geo_ld(g, p, G_DINV10) * v1[p]) * md;
+        gv1[p] = (geo_ld(g, p, G_DINV01) * v0[p] + geo_ld(g, p, G_DINV11) * v1[p]) * md;
+      }
+    }
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) {
+      double dx, dy;
+      deriv_point(gv0, gv1, p / NP, p % NP, dx, dy);
+      sc[p] = (dx + dy) * geo_ld(g, p, G_RMETDET_R);
+    }
+  }
+  if (nu_ratio > 0 && nu_ratio != 1.0) {
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) sc[p] *= nu_ratio;
+  }
+  HXX_UNROLL
+  for (int n = 0; n < NP; ++n) {  // grad_sphere_wk_testcov :714-748
+    HXX_UNROLL
+    for (int m = 0; m < NP; ++m) {
+      const int p = n * NP + m;
+      const double md = geo_ld(g, p, G_METDET);
+      const double mi00 = mi.ld(0 * NPSQ + p), mi01 = mi.ld(1 * NPSQ + p), mi10 = mi.ld(2 * NPSQ + p),
+                   mi11 = mi.ld(3 * NPSQ + p);
+      double b0 = 0.0, b1 = 0.0;
+      HXX_UNROLL
+      for (int j = 0; j < NP; ++j) {
+        const double mpnj = geo_ld(g, n * NP + j, G_MP), mpjm = geo_ld(g, j * NP + m, G_MP);
+        const double snj = sc[n * NP + j], sjm = sc[j * NP + m];
+        const double djm = dc.dvv[j][m], djn = dc.dvv[j][n];
+        const double x0 = mpnj * mi00 * md * snj * djm + mpjm * mi01 * md * sjm * djn;
+        const double x1 = mpnj * mi10 * md * snj * djm + mpjm * mi11 * md * sjm * djn;
+        if (j == 0) { b0 = -x0; b1 = -x1; }
+        else { b0 -= x0; b1 -= x1; }
+      }
+      park0[p * ps] = (geo_ld(g, p, G_D00) * b0 + geo_ld(g, p, G_D10) * b1) * rrearth;
+      park1[p * ps] = (geo_ld(g, p, G_D01) * b0 + geo_ld(g, p, G_D11) * b1) * rrearth;
+    }
+  }
+  phase_fence();
+  {  // vorticity_sphere :494-533, then the mass-weighted copy curl_sphere_wk_testcov works on
+    double c0[NPSQ], c1[NPSQ];
+    {
+      double v0[NPSQ], v1[NPSQ];
+      plane_load(v0p, v0);
+      plane_load(v1p, v1);
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) {
+        c0[p] = geo_ld(g, p, G_D00) * v0[p] + geo_ld(g, p, G_D01) * v1[p];
+        c1[p] = geo_ld(g, p, G_D10) * v0[p] + geo_ld(g, p, G_D11) * v1[p];
+      }
+    }
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) {
+      double dvdx, dudy;
+      deriv_point(c1, c0, p / NP, p % NP, dvdx, dudy);
+      sc[p] = geo_ld(g, p, G_MP) * ((dvdx - dudy) * geo_ld(g, p, G_RMETDET_R));
+    }
+  }
+  phase_fence();
+  {  // curl_sphere_wk_testcov_update(alpha = -1, beta = 1) :683-710 and the final metric term
+    double v0[NPSQ], v1[NPSQ];
+    plane_load(v0p, v0);
+    plane_load(v1p, v1);
+    const double re2 = rrearth * rrearth;
+    HXX_UNROLL
+    for (int n = 0; n < NP; ++n) {
+      HXX_UNROLL
+      for (int m = 0; m < NP; ++m) {
+        const int p = n * NP + m;
+        double sb0 = -(sc[0 * NP + m] * dc.dvv[0][n]);
+        double sb1 = sc[n * NP + 0] * dc.dvv[0][m];
+        HXX_UNROLL
+        for (int j = 1; j < NP; ++j) {
+          sb0 -= sc[j * NP + m] * dc.dvv[j][n];
+          sb1 += sc[n * NP + j] * dc.dvv[j][m];
+        }
+        const double l0 = 1.0 * park0[p * ps] + -1.0 * (geo_ld(g, p, G_D00) * sb0 + geo_ld(g, p, G_D10) * sb1) * rrearth;
+        const double l1 = 1.0 * park1[p * ps] + -1.0 * (geo_ld(g, p, G_D01) * sb0 + geo_ld(g, p, G_D11) * sb1) * rrearth;
+        const double f = 2.0 * geo_ld(g, p, G_SPHEREMP);
+        emit(p, f * v0[p] * re2 + l0, f * v1[p] * re2 + l1);
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ bool is_interior_pt(int p) { return p == 5 || p == 6 || p == 9 || p == 10; }
 
 }  // namespace hxx
