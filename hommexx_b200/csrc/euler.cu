@@ -145,20 +145,32 @@ __global__ void __launch_bounds__(TPB, BIH ? 2 : 4) euler_qminmax_kernel(const E
   cp_async_wait<0>();
 }
 
-// Advection kernel, per-thread storage. Shared-memory slots (slot s of thread t lives at [s][t], so a
-// warp's access to one slot is 256 contiguous bytes): vstar (2x16), dpdissk (16) and its reciprocal
-// (16), plus, on the hyperviscosity stage, one staged plane of the prepared term (16, cp.async).
-// Registers: the limiter weights c (16), the tracer plane being advected (16) and the NEXT tracer's
-// plane (16), whose loads are issued before the limiter starts and land while it runs.
-// two blocks per SM: at three the register cap (168) forces spills that cost more than the extra warps give
+// Advection kernel. A block is 32 consecutive (element, level) lanes x ADV_NW warps: the warps share the
+// lanes' per-level constants of compute_2d_advection_step — vstar (2x16), dpdissk (16), its reciprocal
+// (16) and the limiter weights c = spheremp dpdissk (16), built once per block in shared memory
+// ([slot][lane], a warp's access to one slot is 256 contiguous bytes) — and split the tracers among
+// them (warp w takes q = w, w + ADV_NW, ...). Per-thread state is then the tracer plane being advected,
+// the NEXT tracer's plane (its loads are issued before the limiter starts and land while it runs) and
+// two work planes, which is what lets three blocks (12 warps) live on an SM without spills.
+#ifndef HXX_ADV_NW
+#define HXX_ADV_NW 4
+#endif
 #ifndef HXX_ADV_MINB
-#define HXX_ADV_MINB 2
+#define HXX_ADV_MINB 3
 #endif
 #ifndef HXX_ADV_MINB_HV
-#define HXX_ADV_MINB_HV 2
+#define HXX_ADV_MINB_HV 3
 #endif
+constexpr int ADV_NW = HXX_ADV_NW;
+constexpr int ADV_T = 32 * ADV_NW;
+static_assert(NPSQ % ADV_NW == 0, "the warps split the 16 points of the set-up evenly");
+// per-warp staging slots of the tracer in flight: its qdp plane (16), the two qlim rows, the four
+// time-average partners and, on the hyperviscosity stage, the prepared term (16)
 template <bool HV>
-__host__ __device__ constexpr int advect_slots() { return 64 + (HV ? NPSQ : 0); }
+__host__ __device__ constexpr int advect_stage_slots() { return NPSQ + 2 + 4 + (HV ? NPSQ : 0); }
+// doubles of dynamic shared memory: 5 constant planes + the weight sum, then the warps' staging slots
+template <bool HV>
+__host__ __device__ constexpr int advect_smem_doubles() { return (5 * NPSQ + 1) * 32 + ADV_NW * advect_stage_slots<HV>() * 32; }
 
 // compute_biharmonic_post :216-231 with rhsviss_adjustment :293-310, in place:
 // qtens_biharmonic <- (-rhs_viss dt nu_q) dp0 laplace(qtens_biharmonic) / spheremp
@@ -208,156 +220,152 @@ __global__ void __launch_bounds__(TPB, HXX_HVPOST_MINB) euler_hvpost_kernel(cons
 // advect_and_limit :317-332 = compute_2d_advection_step (:585-626) + run_tracer_phase (:571-582).
 // HV: the hyperviscosity term prepared in place by euler_hvpost_kernel is added (:216-231).
 template <bool HV, bool TAVG>
-__global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) euler_advect_kernel(const EulerArgs a) {
+__global__ void __launch_bounds__(ADV_T, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) euler_advect_kernel(const EulerArgs a) {
   extern __shared__ double s_all[];
-  __shared__ double s_geo[geo_span(TPB) * NPSQ * GEO_N];
-  const int e_first = (int)(((long long)blockIdx.x * TPB) / NLEV);
-  stage_geo<geo_span(TPB), TPB>(s_geo, a.geo, e_first, a.nelem);
-  int ie, k;
-  if (!map_thread(a.nelem, ie, k)) return;  // no block-wide barrier below: early exit is safe
-  const int tid = threadIdx.x;
-  double* const s_vs0 = s_all + tid;
-  double* const s_vs1 = s_all + 16 * TPB + tid;
-  double* const s_dpk = s_all + 32 * TPB + tid;
-  double* const s_rdpk = s_all + 48 * TPB + tid;
-  double* const s_b = s_all + 64 * TPB + tid;  // HV: the prepared term of the tracer in flight
+  __shared__ double s_geo[geo_span(32) * NPSQ * GEO_N];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int e_first = (int)(((long long)blockIdx.x * 32) / NLEV);
+  stage_geo<geo_span(32), ADV_T>(s_geo, a.geo, e_first, a.nelem);
+  // lanes past the last (element, level) pair work on the last valid one and store nothing
+  const long long gl = (long long)blockIdx.x * 32 + lane, glmax = (long long)a.nelem * NLEV - 1;
+  const bool valid = gl <= glmax;
+  const int ie = (int)((valid ? gl : glmax) / NLEV), k = (int)((valid ? gl : glmax) % NLEV);
+  double* const s_vs0 = s_all + lane;
+  double* const s_vs1 = s_all + 16 * 32 + lane;
+  double* const s_dpk = s_all + 32 * 32 + lane;
+  double* const s_rdpk = s_all + 48 * 32 + lane;
+  double* const s_c = s_all + 64 * 32 + lane;
+  double* const s_sumc = s_all + 80 * 32 + lane;
+  double* const s_q = s_all + 81 * 32 + w * advect_stage_slots<HV>() * 32 + lane;  // this warp's staging slots
+  double* const s_l = s_q + NPSQ * 32;  // qlim rows
+  double* const s_a = s_l + 2 * 32;     // time-average partners (qdp_time_avg :379-403, interior points)
+  double* const s_b = s_a + 4 * 32;     // HV: the prepared term
   const GeoShared g{s_geo + (ie - e_first) * NPSQ * GEO_N};
-  const int q0 = blockIdx.y * a.qchunk, q1 = min(a.qsize, q0 + a.qchunk);
   const double* const qin = a.qdp + off_q(ie, a.n0_qdp, 0) + k;
   const double* const qtb = a.qtens_biharmonic + (size_t)ie * QSIZE_D * NLF + k;
   const double* const qlim_in = a.qlim + (size_t)ie * QSIZE_D * 2 * NLEV + k;
   const double* const qavg = TAVG ? a.qdp + off_q(ie, a.tavg_n0, 0) + k : nullptr;
-  auto stage_b = [&](int q) {
-    if (HV) {
-      if (q < q1) {
+  const int q1 = a.qsize;
+  // cp.async (LDGSTS) copies of tracer q into the staging slots: they land while the limiter of the
+  // tracer before it runs, without holding registers
+  auto prefetch = [&](int q) {
+    if (q < q1) {
+      const double* src = qin + (size_t)q * NLF;
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) cp_async8(s_q + p * 32, src + p * NLEV);
+      if (HV) {
         const double* sb = qtb + (size_t)q * NLF;
         HXX_UNROLL
-        for (int p = 0; p < NPSQ; ++p) cp_async8(s_b + p * TPB, sb + p * NLEV);
+        for (int p = 0; p < NPSQ; ++p) cp_async8(s_b + p * 32, sb + p * NLEV);
       }
-      cp_async_commit();
-    }
-  };
-  // next tracer's plane, qlim rows and time-average partners (qdp_time_avg :379-403, interior points)
-  double xn[NPSQ], qmin_n = 0.0, qmax_n = 0.0, qa_n[4] = {0.0, 0.0, 0.0, 0.0};
-  auto load_next = [&](int q) {
-    if (q < q1) {
-      plane_load(qin + (size_t)q * NLF, xn);
-      qmin_n = qlim_in[(size_t)q * 2 * NLEV];
-      qmax_n = qlim_in[(size_t)q * 2 * NLEV + NLEV];
+      cp_async8(s_l, qlim_in + (size_t)q * 2 * NLEV);
+      cp_async8(s_l + 32, qlim_in + (size_t)q * 2 * NLEV + NLEV);
       if (TAVG) {
         const double* pa = qavg + (size_t)q * NLF;
-        qa_n[0] = pa[5 * NLEV]; qa_n[1] = pa[6 * NLEV]; qa_n[2] = pa[9 * NLEV]; qa_n[3] = pa[10 * NLEV];
+        cp_async8(s_a, pa + 5 * NLEV);
+        cp_async8(s_a + 32, pa + 6 * NLEV);
+        cp_async8(s_a + 2 * 32, pa + 9 * NLEV);
+        cp_async8(s_a + 3 * 32, pa + 10 * NLEV);
       }
     }
+    cp_async_commit();
   };
-  stage_b(q0);
+  prefetch(w);
 
+  // set-up, shared by the block's warps: warp w builds points [w PPW, (w + 1) PPW)
+  constexpr int PPW = NPSQ / ADV_NW;
   const bool add_ps_diss = a.nu_p > 0 && HV;
   const double diss_fac = add_ps_diss ? -a.rhs_viss * a.dt * a.nu_q : 0.0;
-  double c[NPSQ];
   {
-    const double* dd = a.derived_dp + off_f(ie) + k;
-    const double* dj = a.divdp_proj + off_f(ie) + k;
-    const double* dv = a.divdp + off_f(ie) + k;
-    const double* n0 = a.derived_vn0 + ((size_t)ie * 2 + 0) * NLF + k;
-    const double* n1 = a.derived_vn0 + ((size_t)ie * 2 + 1) * NLF + k;
-    const double* db = a.dpdiss_biharmonic + off_f(ie) + k;
-    // two rounds of loads, so that no more than four planes are in registers at once
-    double dp[NPSQ];
-    {
-      double r0[NPSQ], r1[NPSQ], r3[NPSQ], r4[NPSQ];
-      plane_load(dd, r0);
-      plane_load(dj, r1);
-      plane_load(n0, r3);
-      plane_load(n1, r4);
-      HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) {
-        dp[p] = r0[p] - a.rhsmdt * r1[p];
-        const double rdp = 1.0 / dp[p];
-        s_vs0[p * TPB] = div_rcp(r3[p], dp[p], rdp);
-        s_vs1[p * TPB] = div_rcp(r4[p], dp[p], rdp);
-      }
-    }
-    phase_fence();
-    {
-      double r2[NPSQ], r5[NPSQ];
-      plane_load(dv, r2);
-      if (add_ps_diss) plane_load(db, r5);
-      HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) {
-        const double sm_ = geo_ld(g, p, G_SPHEREMP);
-        double d = dp[p] - a.dt * r2[p];
-        if (add_ps_diss) d += div_rcp(diss_fac * r5[p], sm_, geo_ld(g, p, G_INV_SPHEREMP));
-        s_dpk[p * TPB] = d;
-        s_rdpk[p * TPB] = 1.0 / d;
-        c[p] = sm_ * d;
-      }
-    }
-  }
-  phase_fence();
-  if (blockIdx.y == 0 && a.f_dss) {  // f_dss *= spheremp (and the interior part of the DSS rspheremp)
-    double* f = a.f_dss + off_f(ie) + k;
-    double r[NPSQ];
-    plane_load(f, r);
+    const size_t o = off_f(ie) + k;
+    double r0[PPW], r1[PPW], r2[PPW], r3[PPW], r4[PPW], r5[PPW], rf[PPW];
     HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) {
-      r[p] = r[p] * geo_ld(g, p, G_SPHEREMP);
-      if (is_interior_pt(p)) r[p] *= geo_ld(g, p, G_RSPHEREMP);
+    for (int i = 0; i < PPW; ++i) {
+      const int p = w * PPW + i;
+      r0[i] = a.derived_dp[o + p * NLEV];
+      r1[i] = a.divdp_proj[o + p * NLEV];
+      r2[i] = a.divdp[o + p * NLEV];
+      r3[i] = a.derived_vn0[((size_t)ie * 2 + 0) * NLF + k + p * NLEV];
+      r4[i] = a.derived_vn0[((size_t)ie * 2 + 1) * NLF + k + p * NLEV];
+      r5[i] = add_ps_diss ? a.dpdiss_biharmonic[o + p * NLEV] : 0.0;
+      rf[i] = a.f_dss ? a.f_dss[o + p * NLEV] : 0.0;
     }
-    plane_store(f, r);
+    HXX_UNROLL
+    for (int i = 0; i < PPW; ++i) {
+      const int p = w * PPW + i;
+      const double sm_ = geo_ld(g, p, G_SPHEREMP);
+      const double dp = r0[i] - a.rhsmdt * r1[i];
+      const double rdp = 1.0 / dp;
+      s_vs0[p * 32] = div_rcp(r3[i], dp, rdp);
+      s_vs1[p * 32] = div_rcp(r4[i], dp, rdp);
+      double d = dp - a.dt * r2[i];
+      if (add_ps_diss) d += div_rcp(diss_fac * r5[i], sm_, geo_ld(g, p, G_INV_SPHEREMP));
+      s_dpk[p * 32] = d;
+      s_rdpk[p * 32] = 1.0 / d;
+      s_c[p * 32] = sm_ * d;
+      if (a.f_dss && valid) {  // f_dss *= spheremp (and the interior part of the DSS rspheremp)
+        double r = rf[i] * sm_;
+        if (is_interior_pt(p)) r *= geo_ld(g, p, G_RSPHEREMP);
+        a.f_dss[o + p * NLEV] = r;
+      }
+    }
   }
-  // the limiter's weight sum does not depend on the tracer (serial order k = 0..15, as the reference)
-  double sumc = c[0];
-  HXX_UNROLL
-  for (int p = 1; p < NPSQ; ++p) sumc += c[p];
+  __syncthreads();
+  if (w == 0) {  // the limiter's weight sum does not depend on the tracer (serial order k = 0..15, as the reference)
+    double sumc = s_c[0];
+    HXX_UNROLL
+    for (int p = 1; p < NPSQ; ++p) sumc += s_c[p * 32];
+    s_sumc[0] = sumc;
+  }
+  __syncthreads();
+  const double sumc = s_sumc[0];
   const bool skip = sumc <= 0;
   const double alpha = -a.dt;
-  double* qlp = a.qlim + ((size_t)ie * QSIZE_D + q0) * 2 * NLEV + k;
-  double* out = a.qdp + off_q(ie, a.np1_qdp, q0) + k;
-  load_next(q0);
-  for (int q = q0; q < q1; ++q, qlp += 2 * NLEV, out += NLF) {
-    const double qmin0 = qmin_n, qmax0 = qmax_n;
-    const double qa[4] = {qa_n[0], qa_n[1], qa_n[2], qa_n[3]};
-    // The qdp plane becomes the advected value in place, one point at a time: with the limiter's
-    // weights that makes four live planes (c, x, gv0, gv1) at the widest spot.
+  for (int q = w; q < q1; q += ADV_NW) {
+    double* const qlp = a.qlim + ((size_t)ie * QSIZE_D + q) * 2 * NLEV + k;
+    double* const out = a.qdp + off_q(ie, a.np1_qdp, q) + k;
+    cp_async_wait<0>();  // this thread's copies of tracer q have landed
+    const double qmin0 = s_l[0], qmax0 = s_l[32];
+    double qa[4] = {0.0, 0.0, 0.0, 0.0};
+    if (TAVG) { qa[0] = s_a[0]; qa[1] = s_a[32]; qa[2] = s_a[2 * 32]; qa[3] = s_a[3 * 32]; }
+    // The qdp plane becomes the advected value in place, one point at a time: three live planes
+    // (x, gv0, gv1) at the widest spot.
     double x[NPSQ];
     HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) x[p] = xn[p];
+    for (int p = 0; p < NPSQ; ++p) x[p] = s_q[p * 32];
     {
       // divergence_sphere_update, SphereOperators.hpp:398-444
       double gv0[NPSQ], gv1[NPSQ];
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) {
-        const double u = s_vs0[p * TPB] * x[p];
-        const double v = s_vs1[p * TPB] * x[p];
+        const double u = s_vs0[p * 32] * x[p];
+        const double v = s_vs1[p * 32] * x[p];
         const double md = geo_ld(g, p, G_METDET);
         gv0[p] = (geo_ld(g, p, G_DINV00) * u + geo_ld(g, p, G_DINV10) * v) * md;
         gv1[p] = (geo_ld(g, p, G_DINV01) * u + geo_ld(g, p, G_DINV11) * v) * md;
       }
-      if (HV) cp_async_wait<0>();  // this thread's copy of the prepared term has landed
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) {
         double dx, dy;
         deriv_point(gv0, gv1, p / NP, p % NP, dx, dy);
         x[p] = x[p] + alpha * ((dx + dy) * geo_ld(g, p, G_RMETDET_R));
-        if (HV) x[p] += s_b[p * TPB];
+        if (HV) x[p] += s_b[p * 32];
       }
     }
-    // the next tracer's loads go out now and land while the limiter runs
-    phase_fence();
-    stage_b(q + 1);
-    load_next(q + 1);
-    phase_fence();
+    // the staged values are in registers: the slots take the next tracer, which lands while the limiter runs
+    prefetch(q + ADV_NW);
     // limiter shell :693-761; a level whose weights do not sum to a positive number is left alone
     if (!skip) {
       double qmin = qmin0, qmax = qmax0;
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) x[p] = div_rcp(x[p], s_dpk[p * TPB], s_rdpk[p * TPB]);
-      limiter_level_w(a.limiter_option, c, sumc, x, qmin, qmax);
+      for (int p = 0; p < NPSQ; ++p) x[p] = div_rcp(x[p], s_dpk[p * 32], s_rdpk[p * 32]);
+      limiter_level_w(a.limiter_option, SlotPlane{s_c, 32}, sumc, x, qmin, qmax);
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) x[p] = x[p] * s_dpk[p * TPB];
-      if (qmin != qmin0) qlp[0] = qmin;
-      if (qmax != qmax0) qlp[NLEV] = qmax;
+      for (int p = 0; p < NPSQ; ++p) x[p] = x[p] * s_dpk[p * 32];
+      if (valid) {
+        if (qmin != qmin0) qlp[0] = qmin;
+        if (qmax != qmax0) qlp[NLEV] = qmax;
+      }
     }
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {  // apply_spheremp :672-687
@@ -366,10 +374,10 @@ __global__ void __launch_bounds__(TPB, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eule
         r *= geo_ld(g, p, G_RSPHEREMP);
         if (TAVG) r = (qa[p == 5 ? 0 : p == 6 ? 1 : p == 9 ? 2 : 3] + 2.0 * r) / 3.0;
       }
-      out[p * NLEV] = r;
+      if (valid) out[p * NLEV] = r;
     }
   }
-  if (HV) cp_async_wait<0>();
+  cp_async_wait<0>();
 }
 
 // f_dss *= spheremp on its own, for the one case where the advection kernel still reads it
@@ -445,12 +453,13 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   a.qlim = S.qlim;  // minmax_exchange swaps the double buffer
   const bool hv = S.rhs_viss != 0.0;
   const bool tavg = tavg_n0_qdp >= 0;
-  const size_t smem = (size_t)(hv ? advect_slots<true>() : advect_slots<false>()) * TPB * sizeof(double);
+  const size_t smem = (size_t)(hv ? advect_smem_doubles<true>() : advect_smem_doubles<false>()) * sizeof(double);
+  const int adv_blocks = (int)(((long long)S.nelemd * NLEV + 31) / 32);
   static bool attr = false;
   if (!attr) {
 #define HXX_ADV_ATTR(H, T)                                                                                  \
   CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                               advect_slots<H>() * TPB * (int)sizeof(double)))
+                               advect_smem_doubles<H>() * (int)sizeof(double)))
     HXX_ADV_ATTR(false, false); HXX_ADV_ATTR(false, true); HXX_ADV_ATTR(true, false); HXX_ADV_ATTR(true, true);
 #undef HXX_ADV_ATTR
     attr = true;
@@ -472,10 +481,10 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   const bool separate = (fdss == S.divdp_proj && a.rhsmdt != 0.0);
   if (separate) a.f_dss = nullptr;
   PROBE(K_EULER_ADVECT);
-  if (hv && tavg) euler_advect_kernel<true, true><<<grid, TPB, smem, S.stream>>>(a);
-  else if (hv) euler_advect_kernel<true, false><<<grid, TPB, smem, S.stream>>>(a);
-  else if (tavg) euler_advect_kernel<false, true><<<grid, TPB, smem, S.stream>>>(a);
-  else euler_advect_kernel<false, false><<<grid, TPB, smem, S.stream>>>(a);
+  if (hv && tavg) euler_advect_kernel<true, true><<<adv_blocks, ADV_T, smem, S.stream>>>(a);
+  else if (hv) euler_advect_kernel<true, false><<<adv_blocks, ADV_T, smem, S.stream>>>(a);
+  else if (tavg) euler_advect_kernel<false, true><<<adv_blocks, ADV_T, smem, S.stream>>>(a);
+  else euler_advect_kernel<false, false><<<adv_blocks, ADV_T, smem, S.stream>>>(a);
   KERNEL_LAUNCHED(K_EULER_ADVECT);
   if (separate) {
     PROBE(K_EULER_FDSS);

@@ -11,8 +11,20 @@ namespace hxx {
 // level is skipped (sum of weights <= 0), in which case x must not be written back.
 // limiter_level_w: the same with the weight sum sumc = c[0] + ... + c[15] (> 0) supplied by the caller,
 // who computes it once for all tracers of a level.
-__device__ __forceinline__ void limiter_level_w(int limiter_option, const double (&c)[NPSQ], double sumc,
-                                                double (&x)[NPSQ], double& qmin, double& qmax) {
+// The weights come through an accessor: a register array (RegPlane) or per-thread shared-memory slots
+// (SlotPlane: point k at base[k * stride]).
+struct RegPlane {
+  const double (&c)[NPSQ];
+  __device__ __forceinline__ double operator[](int k) const { return c[k]; }
+};
+struct SlotPlane {
+  const double* base;
+  int stride;
+  __device__ __forceinline__ double operator[](int k) const { return base[k * stride]; }
+};
+template <class W>
+__device__ __forceinline__ void limiter_level_w(int limiter_option, const W c, double sumc, double (&x)[NPSQ],
+                                                double& qmin, double& qmax) {
   double mass = x[0] * c[0];
 #pragma unroll
   for (int k = 1; k < NPSQ; ++k) mass += x[k] * c[k];
@@ -89,7 +101,7 @@ __device__ __forceinline__ bool limiter_level(int limiter_option, const double (
 #pragma unroll
   for (int k = 1; k < NPSQ; ++k) sumc += c[k];
   if (sumc <= 0) return false;
-  limiter_level_w(limiter_option, c, sumc, x, qmin, qmax);
+  limiter_level_w(limiter_option, RegPlane{c}, sumc, x, qmin, qmax);
   return true;
 }
 
