@@ -145,6 +145,93 @@ __global__ void __launch_bounds__(TPB, BIH ? 2 : 4) euler_qminmax_kernel(const E
   cp_async_wait<0>();
 }
 
+// The hyperviscosity stage's min/max pass (compute_dp + compute_qmin_qmax + compute_biharmonic_pre) in the
+// block shape of the advection kernel below: 32 (element, level) lanes x BIH_NW warps that share dp, its
+// reciprocal and dpdiss_ave in shared memory and split the tracers; each warp stages its tracers'
+// planes two ahead with cp.async. The Laplacian is finished point by point (laplace_points).
+#ifndef HXX_BIH_NW
+#define HXX_BIH_NW 4
+#endif
+#ifndef HXX_BIH_MINB
+#define HXX_BIH_MINB 4
+#endif
+constexpr int BIH_NW = HXX_BIH_NW;
+constexpr int BIH_T = 32 * BIH_NW;
+constexpr int bih_smem_doubles = 3 * NPSQ * 32 + BIH_NW * 2 * NPSQ * 32;
+__global__ void __launch_bounds__(BIH_T, HXX_BIH_MINB) euler_qminmax_bih_kernel(const EulerArgs a) {
+  extern __shared__ double s_all[];
+  __shared__ double s_geo[geo_span(32) * NPSQ * GEO_N];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int e_first = (int)(((long long)blockIdx.x * 32) / NLEV);
+  stage_geo<geo_span(32), BIH_T>(s_geo, a.geo, e_first, a.nelem);
+  const long long gl = (long long)blockIdx.x * 32 + lane, glmax = (long long)a.nelem * NLEV - 1;
+  const bool valid = gl <= glmax;
+  const int ie = (int)((valid ? gl : glmax) / NLEV), k = (int)((valid ? gl : glmax) % NLEV);
+  double* const s_dp = s_all + lane;
+  double* const s_rdp = s_all + 16 * 32 + lane;
+  double* const s_dave = s_all + 32 * 32 + lane;
+  double* const s_q = s_all + 48 * 32 + w * 2 * NPSQ * 32 + lane;  // this warp's [2][16][32] staging
+  const GeoShared g{s_geo + (ie - e_first) * NPSQ * GEO_N};
+  const int q1 = a.qsize;
+  const double* const qin = a.qdp + off_q(ie, a.n0_qdp, 0) + k;
+  auto prefetch = [&](int q, int buf) {
+    if (q < q1) {
+      const double* src = qin + (size_t)q * NLF;
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) cp_async8(s_q + (buf * NPSQ + p) * 32, src + p * NLEV);
+    }
+    cp_async_commit();
+  };
+  prefetch(w, 0);
+  prefetch(w + BIH_NW, 1);
+  const bool scale = a.nu_p > 0;
+  {
+    constexpr int PPW = NPSQ / BIH_NW;
+    const size_t o = off_f(ie) + k;
+    HXX_UNROLL
+    for (int i = 0; i < PPW; ++i) {
+      const int p = w * PPW + i;
+      const double d = a.derived_dp[o + p * NLEV] - a.rhsmdt * a.divdp_proj[o + p * NLEV];
+      s_dp[p * 32] = d;
+      s_rdp[p * 32] = 1.0 / d;
+      if (scale) s_dave[p * 32] = a.dpdiss_ave[o + p * NLEV];
+    }
+  }
+  __syncthreads();
+  const double dp0k = dc.dp0[k], rdp0k = 1.0 / dp0k;
+  int it = 0;
+  for (int q = w; q < q1; q += BIH_NW, ++it) {
+    const int buf = it & 1;
+    double* const ql = a.qlim + ((size_t)ie * QSIZE_D + q) * 2 * NLEV + k;
+    double* const qtb = a.qtens_biharmonic + ((size_t)ie * QSIZE_D + q) * NLF + k;
+    double mn = 0.0, mx = 0.0;
+    if (a.rhs_mode == 1) { mn = ql[0]; mx = ql[NLEV]; }
+    cp_async_wait<1>();
+    double Q[NPSQ];
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) Q[p] = s_q[(buf * NPSQ + p) * 32];
+    prefetch(q + 2 * BIH_NW, buf);
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) Q[p] = div_rcp(Q[p], s_dp[p * 32], s_rdp[p * 32]);
+    if (a.rhs_mode != 1) { mn = Q[0]; mx = Q[0]; }
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) { mn = fmin(mn, Q[p]); mx = fmax(mx, Q[p]); }
+    if (valid) {
+      ql[0] = mn;
+      ql[NLEV] = mx;
+    }
+    if (scale) {
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) Q[p] = div_rcp(Q[p] * s_dave[p * 32], dp0k, rdp0k);
+    }
+    laplace_points<false>(g, nullptr, Q, [&](int p, double lap) {
+      if (is_interior_pt(p)) lap *= geo_ld(g, p, G_RSPHEREMP);  // rspheremp of the DSS that follows
+      if (valid) qtb[p * NLEV] = lap;
+    });
+  }
+  cp_async_wait<0>();
+}
+
 // Advection kernel. A block is 32 consecutive (element, level) lanes x ADV_NW warps: the warps share the
 // lanes' per-level constants of compute_2d_advection_step — vstar (2x16), dpdissk (16), its reciprocal
 // (16) and the limiter weights c = spheremp dpdissk (16), built once per block in shared memory
@@ -204,15 +291,15 @@ __global__ void __launch_bounds__(TPB, HXX_HVPOST_MINB) euler_hvpost_kernel(cons
   for (int q = q0; q < q1; ++q) {
     const int buf = (q - q0) & 1;
     cp_async_wait<1>();
-    double s[NPSQ], lap[NPSQ];
+    double s[NPSQ];
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) s[p] = s_q[(buf * NPSQ + p) * TPB];
     prefetch(q + 2, buf);
-    if (a.consthv) laplace_simple(g, s, lap); else laplace_tensor(g, tv, s, lap);
-    HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p)
-      lap[p] = div_rcp(bfac * dp0k * lap[p], geo_ld(g, p, G_SPHEREMP), geo_ld(g, p, G_INV_SPHEREMP));
-    plane_store(qtb + (size_t)q * NLF, lap);
+    double* const o = qtb + (size_t)q * NLF;
+    auto emit = [&](int p, double lap) {
+      o[p * NLEV] = div_rcp(bfac * dp0k * lap, geo_ld(g, p, G_SPHEREMP), geo_ld(g, p, G_INV_SPHEREMP));
+    };
+    if (a.consthv) laplace_points<false>(g, tv, s, emit); else laplace_points<true>(g, tv, s, emit);
   }
   cp_async_wait<0>();
 }
@@ -438,8 +525,16 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
       CUDA_OK(cudaFuncSetAttribute(euler_qminmax_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bih));
       attr_mm = true;
     }
-    if (mode == 2) euler_qminmax_kernel<true><<<grid, TPB, smem_bih, S.stream>>>(a);
-    else euler_qminmax_kernel<false><<<grid, TPB, smem_mm, S.stream>>>(a);
+    if (mode == 2) {
+      static bool attr_bih = false;
+      if (!attr_bih) {
+        CUDA_OK(cudaFuncSetAttribute(euler_qminmax_bih_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     bih_smem_doubles * (int)sizeof(double)));
+        attr_bih = true;
+      }
+      euler_qminmax_bih_kernel<<<(int)(((long long)S.nelemd * NLEV + 31) / 32), BIH_T, bih_smem_doubles * sizeof(double),
+                                 S.stream>>>(a);
+    } else euler_qminmax_kernel<false><<<grid, TPB, smem_mm, S.stream>>>(a);
   }
   KERNEL_LAUNCHED(K_EULER_QMINMAX);
   if (mode == 0) {
