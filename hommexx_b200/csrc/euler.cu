@@ -248,6 +248,13 @@ __global__ void __launch_bounds__(BIH_T, HXX_BIH_MINB) euler_qminmax_bih_kernel(
 #ifndef HXX_ADV_MINB_HV
 #define HXX_ADV_MINB_HV 3
 #endif
+// 1: the advection kernel of the hyperviscosity stage applies the second Laplacian itself (one pass over
+// qtens_biharmonic less); 0: euler_hvpost_kernel prepares the term in place first. Measured at ne30/q40:
+// fused 50.1 ms per subcycle, split 49.0 ms (the fused kernel's FP64 work no longer hides its latency)
+#ifndef HXX_HV_FUSED
+#define HXX_HV_FUSED 0
+#endif
+constexpr bool HV_FUSED = HXX_HV_FUSED != 0;
 constexpr int ADV_NW = HXX_ADV_NW;
 constexpr int ADV_T = 32 * ADV_NW;
 static_assert(NPSQ % ADV_NW == 0, "the warps split the 16 points of the set-up evenly");
@@ -328,6 +335,7 @@ __global__ void __launch_bounds__(ADV_T, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eu
   double* const s_a = s_l + 2 * 32;     // time-average partners (qdp_time_avg :379-403, interior points)
   double* const s_b = s_a + 4 * 32;     // HV: the prepared term
   const GeoShared g{s_geo + (ie - e_first) * NPSQ * GEO_N};
+  const double* __restrict__ tvis = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
   const double* const qin = a.qdp + off_q(ie, a.n0_qdp, 0) + k;
   const double* const qtb = a.qtens_biharmonic + (size_t)ie * QSIZE_D * NLF + k;
   const double* const qlim_in = a.qlim + (size_t)ie * QSIZE_D * 2 * NLEV + k;
@@ -436,8 +444,27 @@ __global__ void __launch_bounds__(ADV_T, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eu
         double dx, dy;
         deriv_point(gv0, gv1, p / NP, p % NP, dx, dy);
         x[p] = x[p] + alpha * ((dx + dy) * geo_ld(g, p, G_RMETDET_R));
-        if (HV) x[p] += s_b[p * 32];
+        if (HV && !HV_FUSED) x[p] += s_b[p * 32];
       }
+    }
+    if (HV && HV_FUSED) {
+      // compute_biharmonic_post :216-231 with rhsviss_adjustment :293-310 on the fly: the staged plane
+      // is the assembled first Laplacian; its second Laplacian joins x point by point
+      // x waits in the (consumed) staging slots of its tracer while the Laplacian has the registers
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) s_q[p * 32] = x[p];
+      phase_fence();
+      double sb[NPSQ];
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) sb[p] = s_b[p * 32];
+      const double bfac = -a.rhs_viss * a.dt * a.nu_q, dp0k = dc.dp0[k];
+      auto emit = [&](int p, double lap) {
+        s_q[p * 32] += div_rcp(bfac * dp0k * lap, geo_ld(g, p, G_SPHEREMP), geo_ld(g, p, G_INV_SPHEREMP));
+      };
+      if (a.consthv) laplace_points<false>(g, tvis, sb, emit); else laplace_points<true>(g, tvis, sb, emit);
+      phase_fence();
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) x[p] = s_q[p * 32];
     }
     // the staged values are in registers: the slots take the next tracer, which lands while the limiter runs
     prefetch(q + ADV_NW);
@@ -559,7 +586,7 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
 #undef HXX_ADV_ATTR
     attr = true;
   }
-  if (hv) {  // compute_biharmonic_post: the second Laplacian, in place
+  if (hv && !HV_FUSED) {  // compute_biharmonic_post: the second Laplacian, in place
     static bool attr_hp = false;
     if (!attr_hp) {
       CUDA_OK(cudaFuncSetAttribute(euler_hvpost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
