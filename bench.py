@@ -300,14 +300,19 @@ def main():
     adv_bytes = euler_advect_bytes(h.nelemd, cfg.qsize)
     k_avg_ms = k_ms / max(1, nl.value)
     achieved = adv_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
-    traffic = None
+    traffic, fp64_pct = None, None
     tf = ROOT / "profiles" / "roofline_traffic.json"
     if tf.exists():
-        traffic = json.loads(tf.read_text()).get("euler_advect_dram_bytes_per_launch")
+        prof = json.loads(tf.read_text())
+        traffic = prof.get("euler_advect_dram_bytes_per_launch")
+        fp64_pct = prof.get("euler_advect_fp64_pipe_pct")
     roofline = {"bound": "hbm", "kernel": "euler_advect_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": adv_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": nl.value,
-                "kernel_share_of_step": k_ms / ms if ms > 0 else None}
+                "kernel_share_of_step": k_ms / ms if ms > 0 else None,
+                # the kernel's second ceiling (FP64 is uncontracted, --fmad=false): pipe utilisation of its three
+                # stages from the committed ncu capture (profiles/r1z_ncu_summary.txt)
+                "fp64_pipe_pct_ncu": fp64_pct}
     step_bytes = step_bytes_per_elem_step(cfg)
     step_gbs = value / n_gpus * step_bytes / 1e9
 
