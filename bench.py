@@ -114,6 +114,10 @@ def workload(args, n_gpus):
     else:
         ne = int(round((900.0 * n_gpus) ** 0.5))
     over = dict(ne=ne, npart=n_gpus)
+    if ne == 120:  # BASELINE configs[3]: the reference's own ne120 namelist (homme-ne120-v1.nl)
+        if args.qsize:
+            over.update(qsize=args.qsize)
+        return homme.preset("ne120", **over)
     if ne != 30:
         # the namelist's time step and hyperviscosity are tuned to ne30; other meshes follow HOMME's
         # usual scaling (tstep ~ 1/ne, nu ~ dx^3.2: homme-ne120-v1.nl has tstep 75, nu 1e13)
@@ -387,10 +391,10 @@ def main():
     if rank == 0:
         out = {"metric": "element_steps_per_s", "value": value, "unit": "element-steps/s", "n_gpus": n_gpus,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "sypd": sypd, "dynamics_steps_per_bench_step": dyn,
+               "scaling": "strong" if (args.ne and n_gpus > 1) else "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "sypd": sypd, "dynamics_steps_per_bench_step": dyn,
                "config": {"workload": f"preqx ne{cfg.ne} ({h.nelem} elements) nlev{cfg.nlev} qsize{cfg.qsize}, JW baroclinic "
-                                      f"wave, homme-ne30-v1.nl namelist (tstep {cfg.tstep:g} rsplit {cfg.rsplit} qsplit "
+                                      f"wave, homme-ne{120 if cfg.ne == 120 else 30}-v1.nl namelist (tstep {cfg.tstep:g} rsplit {cfg.rsplit} qsplit "
                                       f"{cfg.qsplit} hypervis_subcycle {cfg.hypervis_subcycle} limiter {cfg.limiter_option})",
                           "partition": f"SFC, {n_gpus} part(s), {h.nelemd} elements on rank 0",
                           "l2": "working set (>9 GB at ne30) far exceeds the 126 MB L2; no flush needed",

@@ -37,10 +37,10 @@ __global__ void tracer_forcing_ps_kernel(double* __restrict__ ps_v, const double
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nelem * NPSQ) return;
   const int ie = g / NPSQ, p = g % NPSQ;
-  const double* f = fq + (size_t)ie * QSIZE_D * NLF + p * NLEV;
+  const double* f = fq ? fq + (size_t)ie * QSIZE_D * NLF + p * NLEV : nullptr;
   const double* q = qdp + off_q(ie, np1_qdp, 0) + p * NLEV;
   double acc = 0.0;
-  for (int k = 0; k < NLEV; ++k) acc += clamped_increment(q[k], dt * f[k]);
+  for (int k = 0; k < NLEV; ++k) acc += clamped_increment(q[k], dt * (f ? f[k] : 0.0));
   ps_v[((size_t)ie * NTL + np1) * NPSQ + p] += acc;
 }
 
@@ -59,14 +59,14 @@ __global__ void __launch_bounds__(256) tracer_forcing_kernel(double* __restrict_
   const double rdp = 1.0 / dp;
   double* qd = qdp + off_q(ie, np1_qdp, 0) + i;
   double* out = Q + (size_t)ie * QSIZE_D * NLF + i;
-  const double* f = fq + (size_t)ie * QSIZE_D * NLF + i;
+  const double* f = fq ? fq + (size_t)ie * QSIZE_D * NLF + i : nullptr;  // null: no tracer forcing was ever pushed
   int q = 0;
   for (; q + 4 <= qsize; q += 4) {
     double qs[4], fv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       qs[j] = qd[(size_t)(q + j) * NLF];
-      fv[j] = f[(size_t)(q + j) * NLF];
+      fv[j] = f ? f[(size_t)(q + j) * NLF] : 0.0;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) tracer_forcing_kernel(double* __restrict_
   }
   for (; q < qsize; ++q) {
     const double qs = qd[(size_t)q * NLF];
-    const double r = qs + clamped_increment(qs, dt * f[(size_t)q * NLF]);
+    const double r = qs + clamped_increment(qs, dt * (f ? f[(size_t)q * NLF] : 0.0));
     qd[(size_t)q * NLF] = r;
     out[(size_t)q * NLF] = div_rcp(r, dp, rdp);
   }
@@ -97,7 +97,8 @@ void apply_cam_forcing(double dt, bool tracers) {
   state_forcing_kernel<<<S.nelemd, 288, 0, S.stream>>>(S.v, S.t, S.fm, S.ft, S.n0, dt);
   KERNEL_LAUNCHED(K_FORCING);
   if (!tracers) return;
-  zeros(S.fq, f3 * QSIZE_D);  // CamForcing.cpp:158-160: allocated on first use
+  // CamForcing.cpp:158-160 allocates a zero FQ on first use; here a null FQ means zero tracer forcing, so a
+  // standalone run (which never pushes forcing) neither holds nor reads 40 tiles of zeros per element
   if (S.p.moist) {
     PROBE(K_FORCING);
     tracer_forcing_ps_kernel<<<(S.nelemd * NPSQ + 127) / 128, 128, 0, S.stream>>>(S.ps_v, S.fq, S.qdp, S.nelemd, S.n0,
