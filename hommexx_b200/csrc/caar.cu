@@ -19,7 +19,7 @@ namespace hxx {
 
 struct CaarArgs {
   const double* geo;
-  double *v, *t, *dp3d, *vn0, *omega_p, *phi;
+  double *v, *t, *dp3d, *vn0, *omega_p, *phi, *eta_dot_dpdn;
   const double* qdp;
   int nelem, nm1, n0, np1, n0_qdp;
   double dt, eta_ave_w;
@@ -36,8 +36,10 @@ struct CaarArgs {
 // columns serially (64 threads busy) the others keep the FP64 pipe and the memory system fed.
 constexpr int CAAR_E = HXX_CAAR_E;
 
-template <int E>
-__global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const CaarArgs a) {
+// VADV: rsplit == 0, Eulerian vertical advection (compute_phase_3 :136-148): the interface flux eta_dot_dpdn and
+// the vertical-advection tendencies of T and v take four more shared-memory planes (one block per SM).
+template <int E, bool VADV>
+__global__ void __launch_bounds__(E* NLEV, VADV ? 1 : HXX_CAAR_MINB) caar_kernel(const CaarArgs a) {
   constexpr int LS = NLEV + 1;  // odd column stride: conflict-free column walks
   extern __shared__ double sm[];
   double* s_p = sm;                  // dp -> pressure
@@ -45,6 +47,11 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
   double* s_y = sm + 2 * E * NPSQ * LS;
   double* s_z = sm + 3 * E * NPSQ * LS;
   double* s_w = sm + 4 * E * NPSQ * LS;
+  double* s_e = sm + 5 * E * NPSQ * LS;   // VADV: eta_dot_dpdn at the interface above level k
+  double* s_tv = sm + 6 * E * NPSQ * LS;  // VADV: t_vadv, v_vadv
+  double* s_v0 = sm + 7 * E * NPSQ * LS;
+  double* s_v1 = sm + 8 * E * NPSQ * LS;
+  __shared__ double s_tot[VADV ? E * NPSQ : 1];  // VADV: the column's sdot_sum
   __shared__ double s_geo[E * NPSQ * GEO_N];
   const int tid = threadIdx.x, e = tid / NLEV, k = tid % NLEV;
   // the block's geometry records: every operator below re-reads them, and shared-memory reads do
@@ -116,6 +123,7 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
         }
       }
     }
+    if (VADV) s_tot[tid] = integ;  // assign_zero_to_sdot_sum + the sums of compute_eta_dot_dpdn_vertadv_euler :255-283
   }
   __syncthreads();
 
@@ -140,13 +148,15 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {
       const int slot = (col0 + p) * LS + k;
+      if (VADV)  // compute_eta_dot_dpdn_vertadv_euler :285-299: hybi(k) sdot_sum - (sum of div_vdp above level k)
+        s_e[slot] = k == 0 ? 0.0 : dc.hybi[k] * s_tot[col0 + p] - s_x[slot];
       s_y[slot] = s_x[slot] + 0.5 * div[p];  // integration + 0.5*div_vdp of preq_omega_ps
       s_x[slot] = Rgas * tv[p] * (dp[p] * 0.5 / s_p[slot]);  // preq_hydrostatic :689-729
       s_z[slot] = tv[p];
     }
   }
   // compute_dp3d_np1 :468-493 (eta_dot_dpdn == 0 for rsplit > 0); stored now, dp/div die here
-  if (valid) {
+  if (!VADV && valid) {
     double r[NPSQ];
     plane_load(a.dp3d + off_s(ie, a.nm1) + k, r);
     HXX_UNROLL
@@ -157,6 +167,62 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
     plane_store(a.dp3d + off_s(ie, a.np1) + k, r);
   }
   __syncthreads();
+  if (VADV) {
+    // Every read of a neighbouring level happens here, before the barrier below and hence before any
+    // thread stores T or v at np1 (which may be the n0 level itself).
+    double eta[NPSQ], eta1[NPSQ];
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) {
+      const int slot = (col0 + p) * LS + k;
+      eta[p] = s_e[slot];
+      eta1[p] = k + 1 < NLEV ? s_e[slot + 1] : 0.0;
+    }
+    if (valid) {
+      {  // accumulate_eta_dot_dpdn :150-163
+        double* ed = a.eta_dot_dpdn + off_f(ie) + k;
+        double r[NPSQ];
+        plane_load(ed, r);
+        HXX_UNROLL
+        for (int p = 0; p < NPSQ; ++p) r[p] += a.eta_ave_w * eta[p];
+        plane_store(ed, r);
+      }
+      {  // compute_dp3d_np1 :468-493
+        double r[NPSQ];
+        plane_load(a.dp3d + off_s(ie, a.nm1) + k, r);
+        HXX_UNROLL
+        for (int p = 0; p < NPSQ; ++p) {
+          double tmp = eta1[p];
+          tmp += div[p];
+          tmp -= eta[p];
+          r[p] = geo_ld(g, p, G_SPHEREMP) * (r[p] - tmp * a.dt);
+          if (a.fold_rsp && is_interior_pt(p)) r[p] *= geo_ld(g, p, G_RSPHEREMP);
+        }
+        plane_store(a.dp3d + off_s(ie, a.np1) + k, r);
+      }
+    }
+    // preq_vertadv :495-597 for this level: first / interior / last level forms
+    const double* tp = a.t + off_s(ie, a.n0) + k;
+    HXX_UNROLL
+    for (int p = 0; p < NPSQ; ++p) {
+      const int slot = (col0 + p) * LS + k;
+      const double* f[3] = {tp + p * NLEV, v0p + p * NLEV, v1p + p * NLEV};
+      double* o[3] = {s_tv + slot, s_v0 + slot, s_v1 + slot};
+      double facp = 0.0, facm = 0.0;
+      if (k == 0) facp = (0.5 * 1 / dp[p]) * eta1[p];
+      else if (k == NLEV - 1) facm = (0.5 * (1 / dp[p])) * eta[p];
+      else {
+        facp = 0.5 * (1 / dp[p]) * eta1[p];
+        facm = 0.5 * (1 / dp[p]) * eta[p];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double x0 = f[c][0];
+        if (k == 0) *o[c] = facp * (f[c][1] - x0);
+        else if (k == NLEV - 1) *o[c] = facm * (x0 - f[c][-1]);
+        else *o[c] = facp * (f[c][1] - x0) + facm * (x0 - f[c][-1]);
+      }
+    }
+  }
   if (tid < E * NPSQ) {
     double* cx = s_x + tid * LS;
     const int iec = min(blockIdx.x * E + tid / NPSQ, a.nelem - 1);
@@ -246,8 +312,8 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
       deriv_point(c1, c0, p / NP, p % NP, dvdx, dudy);
       const double vort = (dvdx - dudy) * geo_ld(g, p, G_RMETDET_R);
       const double vt = vort + geo_ld(g, p, G_FCOR);
-      double e0 = -s_p[slot] + v1[p] * vt;
-      double e1 = -s_w[slot] - v0[p] * vt;
+      double e0 = -s_p[slot] + ((VADV ? -s_v0[slot] : 0.0) + v1[p] * vt);
+      double e1 = -s_w[slot] + ((VADV ? -s_v1[slot] : 0.0) - v0[p] * vt);
       e0 = e0 * a.dt + vm0[p * NLEV];
       e1 = e1 * a.dt + vm1[p * NLEV];
       const double sm_ = geo_ld(g, p, G_SPHEREMP);
@@ -283,7 +349,7 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
       double tg0, tg1;
       gradient_point(g, tn0, p, tg0, tg1);
       const double vgrad_t = v0[p] * tg0 + v1[p] * tg1;
-      const double ttens = -vgrad_t + kappa * s_z[slot] * s_y[slot];
+      const double ttens = (VADV ? -s_tv[slot] : 0.0) - vgrad_t + kappa * s_z[slot] * s_y[slot];
       r[p] = ttens * a.dt + r[p];
       r[p] *= geo_ld(g, p, G_SPHEREMP);
       if (a.fold_rsp && is_interior_pt(p)) r[p] *= geo_ld(g, p, G_RSPHEREMP);
@@ -294,16 +360,20 @@ __global__ void __launch_bounds__(E* NLEV, HXX_CAAR_MINB) caar_kernel(const Caar
 
 void caar_run(int nm1, int n0, int np1, double dt, double eta_ave_w, int n0_qdp, bool with_dss) {
   if (!S.nelemd) return;
-  CaarArgs a{S.geo, S.v, S.t, S.dp3d, S.derived_vn0, S.omega_p, S.phi, S.qdp, S.nelemd, nm1, n0, np1, n0_qdp,
+  CaarArgs a{S.geo, S.v, S.t, S.dp3d, S.derived_vn0, S.omega_p, S.phi, S.eta_dot_dpdn, S.qdp, S.nelemd, nm1, n0, np1, n0_qdp,
              dt, eta_ave_w, with_dss ? 1 : 0, S.store_phi ? 1 : 0};
-  constexpr size_t smem = 5 * (size_t)CAAR_E * NPSQ * (NLEV + 1) * sizeof(double);
+  constexpr size_t plane = (size_t)CAAR_E * NPSQ * (NLEV + 1) * sizeof(double);
+  constexpr size_t smem = 5 * plane, smem_vadv = 9 * plane;
   static bool attr = false;
   if (!attr) {
-    CUDA_OK(cudaFuncSetAttribute(caar_kernel<CAAR_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(caar_kernel<CAAR_E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(caar_kernel<CAAR_E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_vadv));
     attr = true;
   }
+  const int nb = (S.nelemd + CAAR_E - 1) / CAAR_E;
   PROBE(K_CAAR);
-  caar_kernel<CAAR_E><<<(S.nelemd + CAAR_E - 1) / CAAR_E, CAAR_E * NLEV, smem, S.stream>>>(a);
+  if (S.p.rsplit == 0) caar_kernel<CAAR_E, true><<<nb, CAAR_E * NLEV, smem_vadv, S.stream>>>(a);
+  else caar_kernel<CAAR_E, false><<<nb, CAAR_E * NLEV, smem, S.stream>>>(a);
   KERNEL_LAUNCHED(K_CAAR);
   if (with_dss) dss_exchange(fields_caar(np1), true);  // CaarFunctor.cpp:113
 }

@@ -278,7 +278,7 @@ void prim_diag_scalars(bool before_advance, int ivar);
 void prim_energy_halftimes(bool before_advance, int ivar);
 void push_Q_to_host(double* host_q);  // hxx_session.cu: device Q -> F90 layout
 // remap.cu
-void vertical_remap(int np1, int np1_qdp);
+void vertical_remap(int np1, int np1_qdp, double dt);
 void check_remap_flag();
 
 }  // namespace hxx

@@ -438,8 +438,6 @@ void init_simulation_params_c(const int* remap_alg, const int* limiter_option, c
   if (!(*nu > 0.0)) option_error(loc, "nu", *nu);
   if (!(*nu_div > 0.0)) option_error(loc, "nu_div", *nu_div);
   if (*qsize > QSIZE_D) runtime_abort("init_simulation_params_c: qsize exceeds the QSIZE_D of this build", 13);
-  if (*rsplit == 0)
-    runtime_abort("init_simulation_params_c: rsplit=0 (Eulerian vertical advection) is not built yet; see DESIGN.md", 12);
   Params& p = S.p;
   p.remap_alg = *remap_alg; p.limiter_option = *limiter_option; p.rsplit = *rsplit; p.qsplit = *qsplit;
   p.time_step_type = *time_step_type; p.qsize = *qsize; p.state_frequency = *state_frequency;
@@ -596,7 +594,7 @@ void prim_run_subcycle_c(const double* dt, int* nstep, int* nm1, int* n0, int* n
   update_tracers_levels();
   // :131 and :138 — the remap kernel also stores Q = Qdp / dp for every tracer (update_q fused
   // into its tracer store); without tracers there is nothing to update
-  vertical_remap(S.np1, S.np1_qdp);
+  vertical_remap(S.np1, S.np1_qdp, dt_remap);
   check_remap_flag();                // RemapFunctor.hpp:190-198 (one host sync per call)
   if (compute_diagnostics) {
     prim_diag_scalars(false, 1);
@@ -665,8 +663,7 @@ void hxx_euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, i
 }
 void hxx_euler_qdp_time_avg(int n0_qdp, int np1_qdp) { euler_qdp_time_avg(n0_qdp, np1_qdp); }
 void hxx_vertical_remap(int np1, int np1_qdp, double dt) {
-  (void)dt;
-  vertical_remap(np1, np1_qdp);
+  vertical_remap(np1, np1_qdp, dt);
   check_remap_flag();
 }
 void hxx_update_q(int np1_qdp, int np1) { update_q(np1_qdp, np1); }

@@ -363,8 +363,63 @@ __global__ void __launch_bounds__(REMAP_MAX_WARPS * 32) remap_kernel(const Remap
   cp_async_wait<0>();
 }
 
-void vertical_remap(int np1, int np1_qdp) {
+// rsplit == 0 (RemapFunctor.hpp:42-100): the dynamics stay on reference levels, so only the tracers are
+// remapped, from source thickness = reference thickness + dt (eta_dot_dpdn(k+1) - eta_dot_dpdn(k)). Off the
+// benchmark path: one block per column, warp 0 builds the grids, one thread per tracer sweeps the column
+// with the production ppm_sweep (plain loads / stores), update_q fused as in the main kernel.
+__global__ void __launch_bounds__(64) remap_eulerian_kernel(const RemapArgs a, const double* __restrict__ eta_dot_dpdn,
+                                                            double dt) {
+  __shared__ ColData c;
+  __shared__ double scratch[2 * NLEV + 3];
+  const int ie = blockIdx.x / NPSQ, p = blockIdx.x % NPSQ, lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    const double* dp = a.dp3d + off_s(ie, a.np1) + p * NLEV;
+    const double* eta = eta_dot_dpdn + off_f(ie) + p * NLEV;
+    double ps = 0.0;
+    if (lane == 0) {  // compute_ps_v :367-385 (serial sum, k ascending)
+      for (int k = 0; k < NLEV; ++k) ps += dp[k];
+      ps += dc.hyai0 * dc.ps0;
+      a.ps_v[((size_t)ie * NTL + a.np1) * NPSQ + p] = ps;
+    }
+    ps = __shfl_sync(0xffffffffu, ps, 0);
+    bool bad = false;
+    for (int k = lane; k < NLEV; k += 32) {
+      const double tgt = dc.dai[k] * dc.ps0 + dc.dbi[k] * ps;  // compute_target_thickness :417-437
+      const double eta_next = k + 1 < NLEV ? eta[k + 1] : 0.0;
+      const double delta_dpdn = eta_next - eta[k];
+      const double src = tgt + dt * delta_dpdn;                // compute_source_thickness :60-92
+      c.tgt[k] = tgt;
+      c.dpo[k + PAD] = src;
+      bad |= (isnan(src) || src < 0.0);                        // check_source_thickness :439-464
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    __syncwarp();
+    if (bad) {
+      if (lane == 0) { atomicOr(a.invalid, 1); c.ok = 0; }
+    } else {
+      if (lane == 0) c.ok = 1;
+      if (!ppm_column_grids(c, scratch, lane) && lane == 0) atomicOr(a.invalid, 1);
+    }
+  }
+  __syncthreads();
+  if (!c.ok) return;
+  for (int q = threadIdx.x; q < a.qsize; q += blockDim.x) {
+    double* fld = a.qdp + off_q(ie, a.np1_qdp, q) + p * NLEV;
+    double* Qf = a.Q + (((size_t)ie * QSIZE_D + q) * NPSQ + p) * NLEV;
+    ppm_sweep(c, a.alg, true, false, [](int) {}, [&](int k) { return fld[k]; },
+              [&](int k, double x, double over_tgt) { fld[k] = x; Qf[k] = over_tgt; });
+  }
+}
+
+void vertical_remap(int np1, int np1_qdp, double dt) {
   if (!S.nelemd) return;
+  if (S.p.rsplit == 0) {
+    RemapArgs a{S.v, S.t, S.dp3d, S.ps_v, S.qdp, S.Q, S.nelemd, np1, np1_qdp, S.p.qsize, S.p.remap_alg, S.invalid_flag};
+    PROBE(K_REMAP);
+    remap_eulerian_kernel<<<(unsigned)(S.nelemd * NPSQ), 64, 0, S.stream>>>(a, S.eta_dot_dpdn, dt);
+    KERNEL_LAUNCHED(K_REMAP);
+    return;
+  }
   RemapArgs a{S.v, S.t, S.dp3d, S.ps_v, S.qdp, S.Q, S.nelemd, np1, np1_qdp, S.p.qsize, S.p.remap_alg, S.invalid_flag};
   const RemapMap m = remap_map(S.p.qsize);
   const size_t smem = RC * sizeof(ColData) + (size_t)m.nwarps * STAGE_PER_WARP * sizeof(double);

@@ -747,7 +747,7 @@ static void exchange_min_max(void) {
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* CAAR (CaarFunctorImpl.hpp), rsplit > 0 path                                                 */
+/* CAAR (CaarFunctorImpl.hpp)                                                                  */
 /* ------------------------------------------------------------------------------------------ */
 #define VFLD(ie, tl, c) (O.v + (((size_t)(ie) * NTL + (tl)) * 2 + (c)) * NLF)
 #define TFLD(ie, tl) (O.t + ((size_t)(ie) * NTL + (tl)) * NLF)
@@ -756,7 +756,7 @@ static void exchange_min_max(void) {
 
 static void caar_element(int ie, int nm1, int n0, int np1, double dt, double eta_ave_w, int n0_qdp) {
   const int nlev = O.nlev;
-  double* buf = (double*)malloc(16 * NLF * sizeof(double));
+  double* buf = (double*)malloc(18 * NLF * sizeof(double));
   double *t_virt = buf, *vdp0 = buf + NLF, *vdp1 = buf + 2 * NLF, *div_vdp = buf + 3 * NLF, *pressure = buf + 4 * NLF,
          *pgrad0 = buf + 5 * NLF, *pgrad1 = buf + 6 * NLF, *omega_p = buf + 7 * NLF, *tgrad0 = buf + 8 * NLF,
          *tgrad1 = buf + 9 * NLF, *egrad0 = buf + 10 * NLF, *egrad1 = buf + 11 * NLF, *ephi = buf + 12 * NLF,
@@ -819,7 +819,44 @@ static void caar_element(int ie, int nm1, int n0, int np1, double dt, double eta
     }
   }
 
-  /* compute_phase_3 :136-148 (rsplit > 0: no vertical advection) */
+  /* compute_phase_3 :136-148; rsplit == 0: Eulerian vertical advection */
+  double *eta_buf = buf + 14 * NLF, *t_vadv = buf + 15 * NLF, *v_vadv0 = buf + 16 * NLF, *v_vadv1 = buf + 17 * NLF;
+  const bool vadv = (O.rsplit == 0);
+  if (vadv) {
+    for (int p = 0; p < NPSQ; ++p) {
+      /* assign_zero_to_sdot_sum + compute_eta_dot_dpdn_vertadv_euler :255-300 */
+      double sdot = 0;
+      for (int k = 0; k < nlev - 1; ++k) {
+        sdot += div_vdp[IX(p, k)];
+        eta_buf[IX(p, k + 1)] = sdot;
+      }
+      sdot += div_vdp[IX(p, nlev - 1)];
+      for (int k = 1; k < nlev; ++k) eta_buf[IX(p, k)] = O.hybi[k] * sdot - eta_buf[IX(p, k)];
+      eta_buf[IX(p, 0)] = 0.0;
+      /* preq_vertadv :495-597 */
+      {
+        double facp = (0.5 * 1 / dp0[IX(p, 0)]) * eta_buf[IX(p, 1)], facm;
+        t_vadv[IX(p, 0)] = facp * (t0[IX(p, 1)] - t0[IX(p, 0)]);
+        v_vadv0[IX(p, 0)] = facp * (v0[IX(p, 1)] - v0[IX(p, 0)]);
+        v_vadv1[IX(p, 0)] = facp * (v1[IX(p, 1)] - v1[IX(p, 0)]);
+        for (int k = 1; k < nlev - 1; ++k) {
+          facp = 0.5 * (1 / dp0[IX(p, k)]) * eta_buf[IX(p, k + 1)];
+          facm = 0.5 * (1 / dp0[IX(p, k)]) * eta_buf[IX(p, k)];
+          t_vadv[IX(p, k)] = facp * (t0[IX(p, k + 1)] - t0[IX(p, k)]) + facm * (t0[IX(p, k)] - t0[IX(p, k - 1)]);
+          v_vadv0[IX(p, k)] = facp * (v0[IX(p, k + 1)] - v0[IX(p, k)]) + facm * (v0[IX(p, k)] - v0[IX(p, k - 1)]);
+          v_vadv1[IX(p, k)] = facp * (v1[IX(p, k + 1)] - v1[IX(p, k)]) + facm * (v1[IX(p, k)] - v1[IX(p, k - 1)]);
+        }
+        const int k = nlev - 1;
+        facm = (0.5 * (1 / dp0[IX(p, k)])) * eta_buf[IX(p, k)];
+        t_vadv[IX(p, k)] = facm * (t0[IX(p, k)] - t0[IX(p, k - 1)]);
+        v_vadv0[IX(p, k)] = facm * (v0[IX(p, k)] - v0[IX(p, k - 1)]);
+        v_vadv1[IX(p, k)] = facm * (v1[IX(p, k)] - v1[IX(p, k - 1)]);
+      }
+    }
+    /* accumulate_eta_dot_dpdn :150-163 */
+    double* eta = O.eta_dot_dpdn + F3(ie);
+    for (size_t i = 0; i < NLF; ++i) eta[i] += eta_ave_w * eta_buf[i];
+  }
   /* compute_omega_p :412-423 */
   double* om = O.omega_p + F3(ie);
   for (size_t i = 0; i < NLF; ++i) om[i] += eta_ave_w * omega_p[i];
@@ -833,7 +870,7 @@ static void caar_element(int ie, int nm1, int n0, int np1, double dt, double eta
       for (int k = 0; k < nlev; ++k) {
         const size_t i = IX(p, k);
         const double vgrad_t = v0[i] * tgrad0[i] + v1[i] * tgrad1[i];
-        const double ttens = 0 - vgrad_t + kappa * t_virt[i] * omega_p[i];
+        const double ttens = (vadv ? -t_vadv[i] : 0) - vgrad_t + kappa * t_virt[i] * omega_p[i];
         double temp_np1 = ttens * dt + tm1[i];
         temp_np1 *= S2(O.spheremp, ie, p);
         tp1[i] = temp_np1;
@@ -856,9 +893,9 @@ static void caar_element(int ie, int nm1, int n0, int np1, double dt, double eta
         const size_t i = IX(p, k);
         vort[i] += S2(O.fcor, ie, p);
         egrad0[i] *= -1;
-        egrad0[i] += 0 + v1[i] * vort[i];
+        egrad0[i] += (vadv ? -v_vadv0[i] : 0) + v1[i] * vort[i];
         egrad1[i] *= -1;
-        egrad1[i] += 0 - v0[i] * vort[i];
+        egrad1[i] += (vadv ? -v_vadv1[i] : 0) - v0[i] * vort[i];
         egrad0[i] *= dt;
         egrad0[i] += vm0[i];
         egrad1[i] *= dt;
@@ -878,9 +915,9 @@ static void caar_element(int ie, int nm1, int n0, int np1, double dt, double eta
     for (int p = 0; p < NPSQ; ++p)
       for (int k = 0; k < nlev; ++k) {
         const size_t i = IX(p, k);
-        double tmp = 0.0;
+        double tmp = (vadv && k + 1 < nlev) ? eta_buf[IX(p, k + 1)] : 0.0;
         tmp += div_vdp[i];
-        tmp -= 0.0;
+        tmp -= vadv ? eta_buf[i] : 0.0;
         tmp = dpm1[i] - tmp * dt;
         dpp1[i] = S2(O.spheremp, ie, p) * tmp;
       }
@@ -889,7 +926,6 @@ static void caar_element(int ie, int nm1, int n0, int np1, double dt, double eta
 }
 
 void hxx_caar_run(int nm1, int n0, int np1, double dt, double eta_ave_w, int n0_qdp, int with_dss) {
-  if (O.rsplit == 0) runtime_abort("oracle: rsplit=0 (Eulerian vertical) is not on the hot path (SURVEY 8f)", 12);
 #pragma omp parallel for
   for (int ie = 0; ie < O.nelemd; ++ie) caar_element(ie, nm1, n0, np1, dt, eta_ave_w, n0_qdp);
   if (with_dss) {
@@ -1417,34 +1453,48 @@ void hxx_remap_columns(int alg, int ncols, int nfields, const double* src_dp, co
   }
 }
 
-/* RemapFunctor::run_remap :306-331 (nonzero rsplit) */
+/* RemapFunctor::run_remap :306-331. rsplit == 0 (:42-100): the source thickness is the reference thickness
+   plus dt times the increment of the mean vertical flux, and only the tracers are remapped. */
 void hxx_vertical_remap(int np1, int np1_qdp, double dt) {
-  (void)dt;
   const int nlev = O.nlev, n = O.nelemd, nq = O.qsize;
+  const bool lagrangian = O.rsplit > 0;
   int invalid_any = 0;
 #pragma omp parallel for reduction(| : invalid_any)
   for (int ie = 0; ie < n; ++ie) {
-    double* tgt = (double*)malloc(NLF * sizeof(double));
+    double* tgt = (double*)malloc(2 * NLF * sizeof(double));
     const double* src = DPFLD(ie, np1);
+    const double* dp_np1 = src;
     double* ps = O.ps_v + ((size_t)ie * NTL + np1) * NPSQ;
     /* compute_ps_v :367-385 */
     for (int p = 0; p < NPSQ; ++p) {
       ps[p] = 0.0;
-      for (int k = 0; k < nlev; ++k) ps[p] += src[IX(p, k)];
+      for (int k = 0; k < nlev; ++k) ps[p] += dp_np1[IX(p, k)];
       ps[p] += O.hyai0 * O.ps0;
     }
     /* compute_target_thickness :417-437 */
     for (int p = 0; p < NPSQ; ++p)
       for (int k = 0; k < nlev; ++k)
         tgt[IX(p, k)] = (O.hyai[k + 1] - O.hyai[k]) * O.ps0 + (O.hybi[k + 1] - O.hybi[k]) * ps[p];
+    if (!lagrangian) { /* compute_source_thickness :60-92 */
+      double* s0 = tgt + NLF;
+      const double* eta = O.eta_dot_dpdn + F3(ie);
+      for (int p = 0; p < NPSQ; ++p)
+        for (int k = 0; k < nlev; ++k) {
+          const double eta_next = k + 1 < nlev ? eta[IX(p, k + 1)] : 0;
+          const double delta_dpdn = eta_next - eta[IX(p, k)];
+          s0[IX(p, k)] = tgt[IX(p, k)] + dt * delta_dpdn;
+        }
+      src = s0;
+    }
     /* check_source_thickness :439-464 */
     int invalid = 0;
     for (size_t i = 0; i < NLF; ++i) invalid |= (isnan(src[i]) || src[i] < 0.0);
     invalid_any |= invalid;
-    if (!invalid && (nq + 3) > 0) {
+    const int nst = lagrangian ? 3 : 0;
+    if (!invalid && (nq + nst) > 0) {
       /* ComputeExtrinsicsTag :255-268 */
       double* st[3] = {VFLD(ie, np1, 0), VFLD(ie, np1, 1), TFLD(ie, np1)};
-      for (int s = 0; s < 3; ++s)
+      for (int s = 0; s < nst; ++s)
         for (size_t i = 0; i < NLF; ++i) st[s][i] *= src[i];
       double* g = (double*)malloc(sizeof(double) * ((nlev + 4) + (nlev + 2) + (nlev + 1) + 10 * (nlev + 2) + nlev + 8 * (nlev + 4)));
       double *dpo = g, *pio = dpo + nlev + 4, *pin = pio + nlev + 2, *ppmdx = pin + nlev + 1, *z2 = ppmdx + 10 * (nlev + 2),
@@ -1452,14 +1502,14 @@ void hxx_vertical_remap(int np1, int np1_qdp, double dt) {
       int* kid = (int*)malloc(sizeof(int) * nlev);
       for (int p = 0; p < NPSQ; ++p) {
         ppm_column_grids(nlev, src + IX(p, 0), 1, tgt + IX(p, 0), 1, dpo, pio, pin, ppmdx, z2, kid);
-        for (int s = 0; s < 3; ++s) ppm_column_remap(O.remap_alg, nlev, dpo, ppmdx, z2, kid, st[s] + IX(p, 0), 1, work);
+        for (int s = 0; s < nst; ++s) ppm_column_remap(O.remap_alg, nlev, dpo, ppmdx, z2, kid, st[s] + IX(p, 0), 1, work);
         for (int q = 0; q < nq; ++q)
           ppm_column_remap(O.remap_alg, nlev, dpo, ppmdx, z2, kid, QDPFLD(ie, np1_qdp, q) + IX(p, 0), 1, work);
       }
       free(kid);
       free(g);
       /* ComputeIntrinsicsTag :294-307 */
-      for (int s = 0; s < 3; ++s)
+      for (int s = 0; s < nst; ++s)
         for (size_t i = 0; i < NLF; ++i) st[s][i] /= tgt[i];
     }
     free(tgt);

@@ -93,12 +93,35 @@ def test_remap_and_update_q_parity(warm_pair):
     assert np.allclose(qdp1[:, 1].sum(-1), qdp0[:, 1].sum(-1), rtol=1e-13, atol=0)
 
 
+def test_caar_eulerian_vertical_parity():
+    """rsplit = 0: every RK stage shape of CAAR with the vertical-advection terms, then the tracer-only remap."""
+    cfg = homme.preset("ne4", rsplit=0)
+    hc, ho = parity.pair(cfg)
+    ho.run_subcycle()
+    snap = {n: ho.get_field(n) for n in parity.STATE_FIELDS}
+    for (nm1, n0, np1, dt, w, dss) in [(1, 1, 0, 360.0, 0.25, 0), (1, 0, 2, 360.0, 0.0, 1), (1, 2, 2, 600.0, 0.0, 1),
+                                       (0, 2, 2, 1350.0, 0.75, 1)]:
+        for h in (hc, ho):
+            for n, a in snap.items():
+                h.set_field(n, a)
+            h.lib.hxx_caar_run(nm1, n0, np1, dt, w, -1, dss)
+        parity.compare_fields(hc, ho, parity.STATE_FIELDS + ["phi"], tol=0.0, what=f"caar rsplit=0 {(nm1, n0, np1, dss)}")
+    for h in (hc, ho):
+        h.lib.hxx_vertical_remap(2, 1, 1800.0)
+        h.lib.hxx_update_q(1, 2)   # fused into the CUDA remap's tracer store; a separate pass in the oracle
+    parity.compare_fields(hc, ho, tol=0.0, what="eulerian remap")
+    hc.close(); ho.close()
+
+
 CASES = {
     "ne4": dict(),                                              # BASELINE configs[0]: ne4, nlev 72, qsize 4
     "prtcA": dict(),                                            # the reference's prtcA_c sizes: nlev 26, qsize 4
     "prtcA-lim9-alg2": dict(base="prtcA", limiter_option=9, remap_alg=2),
     "prtcA-moist-nudiv-q2": dict(base="prtcA", moisture=1, nu_div=1.75e16, qsplit=2, rsplit=2),
     "ne8": dict(),
+    # rsplit = 0: Eulerian vertical advection in CAAR, tracer-only remap (test-list.cmake's r0 variants)
+    "ne4-r0": dict(base="ne4", rsplit=0),
+    "prtcA-r0-moist-q3": dict(base="prtcA", rsplit=0, moisture=1, qsplit=3),
 }
 
 
