@@ -14,6 +14,9 @@
  * test/unit_tests/inputs/{gradient,divergence,vorticity}_sphere_np4.in; bitwise agreement
  * of the PPM remap with the reference's own plain-C++ twin src/preqx/unit_tests/remap.cpp
  * compiled into oracle/_ref/; the limiter property tests of preqx_ut.cpp:1335-1531.
+ * CAM forcing and diagnostics are checked against a direct numpy restatement of the reference
+ * formulas (tests/test_oracle_forcing_diag.py); the rsplit = 0 path against the vertically Lagrangian
+ * one (tests/test_oracle_rsplit0.py: same equations, different discretisation, truncation-error agreement).
  * There is no stored whole-timestep output in the reference, so whole-step parity of the
  * CUDA path is oracle-vs-CUDA.
  */
