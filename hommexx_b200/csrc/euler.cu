@@ -211,8 +211,7 @@ __global__ void __launch_bounds__(BIH_T, HXX_BIH_MINB) euler_qminmax_bih_kernel(
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) Q[p] = s_q[(buf * NPSQ + p) * 32];
     prefetch(q + 2 * BIH_NW, buf);
-    HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) Q[p] = div_rcp(Q[p], s_dp[p * 32], s_rdp[p * 32]);
+    div_rcp_plane(Q, [&](int p) { return s_dp[p * 32]; }, [&](int p) { return s_rdp[p * 32]; });
     if (a.rhs_mode != 1) { mn = Q[0]; mx = Q[0]; }
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) { mn = fmin(mn, Q[p]); mx = fmax(mx, Q[p]); }
@@ -471,8 +470,7 @@ __global__ void __launch_bounds__(ADV_T, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eu
     // limiter shell :693-761; a level whose weights do not sum to a positive number is left alone
     if (!skip) {
       double qmin = qmin0, qmax = qmax0;
-      HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) x[p] = div_rcp(x[p], s_dpk[p * 32], s_rdpk[p * 32]);
+      div_rcp_plane(x, [&](int p) { return s_dpk[p * 32]; }, [&](int p) { return s_rdpk[p * 32]; });
       limiter_level_w(a.limiter_option, SlotPlane{s_c, 32}, sumc, x, qmin, qmax);
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) x[p] = x[p] * s_dpk[p * 32];

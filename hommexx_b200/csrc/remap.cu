@@ -26,6 +26,12 @@ HXX_DEFINE_CONSTANTS()
 
 namespace hxx {
 
+// unroll of the sweep: the register window rotates with periods 3 (cell means) and 2 (masses), so 6 removes
+// the register moves of the rotation
+#ifndef HXX_REMAP_UNROLL
+#define HXX_REMAP_UNROLL 2
+#endif
+constexpr int REMAP_UNROLL = HXX_REMAP_UNROLL;
 constexpr int PAD = 2;
 constexpr int RC = 4;        // columns per block
 constexpr int CH = 4;        // levels per staged chunk (32 B per column-field)
@@ -183,7 +189,7 @@ __device__ __forceinline__ void ppm_sweep(const ColData& c, int alg, bool active
     AI0 = ppm_ai(A0, Am1, DM0, dm_m1, c.p3[0], c.p4[0], c.p567[0], c.p8[0], c.p9[0]);
     kid_next = c.kid[0];
   }
-#pragma unroll 2
+#pragma unroll REMAP_UNROLL
   for (int cc = 0; cc < NLEV - 2; ++cc) {
     const int ln = cc + 2;  // level entering the window
     tick(ln);
