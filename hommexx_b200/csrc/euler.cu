@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(BIH_T, HXX_BIH_MINB) euler_qminmax_bih_kernel(
     }
     if (scale) {
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) Q[p] = div_rcp(Q[p] * s_dave[p * 32], dp0k, rdp0k);
+      for (int p = 0; p < NPSQ; ++p) Q[p] = Q[p] * s_dave[p * 32];
+      div_rcp_plane(Q, [&](int) { return dp0k; }, [&](int) { return rdp0k; });
     }
     laplace_points<false>(g, nullptr, Q, [&](int p, double lap) {
       if (is_interior_pt(p)) lap *= geo_ld(g, p, G_RSPHEREMP);  // rspheremp of the DSS that follows
@@ -301,11 +302,11 @@ __global__ void __launch_bounds__(TPB, HXX_HVPOST_MINB) euler_hvpost_kernel(cons
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) s[p] = s_q[(buf * NPSQ + p) * TPB];
     prefetch(q + 2, buf);
-    double* const o = qtb + (size_t)q * NLF;
-    auto emit = [&](int p, double lap) {
-      o[p * NLEV] = div_rcp(bfac * dp0k * lap, geo_ld(g, p, G_SPHEREMP), geo_ld(g, p, G_INV_SPHEREMP));
-    };
+    double t[NPSQ];
+    auto emit = [&](int p, double lap) { t[p] = bfac * dp0k * lap; };
     if (a.consthv) laplace_points<false>(g, tv, s, emit); else laplace_points<true>(g, tv, s, emit);
+    div_rcp_plane(t, [&](int p) { return geo_ld(g, p, G_SPHEREMP); }, [&](int p) { return geo_ld(g, p, G_INV_SPHEREMP); });
+    plane_store(qtb + (size_t)q * NLF, t);
   }
   cp_async_wait<0>();
 }

@@ -153,8 +153,12 @@ __global__ void __launch_bounds__(TPB, SPONGE ? 2 : 3) hv_second_scalar_kernel(c
       double* dave = a.dpdiss_ave + off_f(ie) + k;
       double r0[NPSQ];
       plane_load(dave, r0);
+      double t[NPSQ];
       HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) r0[p] += div_rcp(a.eta_ave_w * dp[p], hs, rhs);
+      for (int p = 0; p < NPSQ; ++p) t[p] = a.eta_ave_w * dp[p];
+      div_rcp_plane(t, [&](int) { return hs; }, [&](int) { return rhs; });
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) r0[p] += t[p];
       plane_store(dave, r0);
     }
     if constexpr (SPONGE) laplace_simple(g, dp, top);
