@@ -152,18 +152,23 @@ __global__ void __launch_bounds__(TPB, BIH ? 2 : 4) euler_qminmax_kernel(const E
 #ifndef HXX_BIH_NW
 #define HXX_BIH_NW 4
 #endif
+// 1: stages 1 and 2 use the same block shape (reciprocal division); 0: the thread-local kernel above
+#ifndef HXX_QMM_SHARED
+#define HXX_QMM_SHARED 1
+#endif
 #ifndef HXX_BIH_MINB
 #define HXX_BIH_MINB 4
 #endif
 constexpr int BIH_NW = HXX_BIH_NW;
 constexpr int BIH_T = 32 * BIH_NW;
 constexpr int bih_smem_doubles = 3 * NPSQ * 32 + BIH_NW * 2 * NPSQ * 32;
+template <bool BIH>
 __global__ void __launch_bounds__(BIH_T, HXX_BIH_MINB) euler_qminmax_bih_kernel(const EulerArgs a) {
   extern __shared__ double s_all[];
   __shared__ double s_geo[geo_span(32) * NPSQ * GEO_N];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int e_first = (int)(((long long)blockIdx.x * 32) / NLEV);
-  stage_geo<geo_span(32), BIH_T>(s_geo, a.geo, e_first, a.nelem);
+  if (BIH) stage_geo<geo_span(32), BIH_T>(s_geo, a.geo, e_first, a.nelem);
   const long long gl = (long long)blockIdx.x * 32 + lane, glmax = (long long)a.nelem * NLEV - 1;
   const bool valid = gl <= glmax;
   const int ie = (int)((valid ? gl : glmax) / NLEV), k = (int)((valid ? gl : glmax) % NLEV);
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(BIH_T, HXX_BIH_MINB) euler_qminmax_bih_kernel(
   };
   prefetch(w, 0);
   prefetch(w + BIH_NW, 1);
-  const bool scale = a.nu_p > 0;
+  const bool scale = BIH && a.nu_p > 0;
   {
     constexpr int PPW = NPSQ / BIH_NW;
     const size_t o = off_f(ie) + k;
@@ -224,10 +229,11 @@ __global__ void __launch_bounds__(BIH_T, HXX_BIH_MINB) euler_qminmax_bih_kernel(
       for (int p = 0; p < NPSQ; ++p) Q[p] = Q[p] * s_dave[p * 32];
       div_rcp_plane(Q, [&](int) { return dp0k; }, [&](int) { return rdp0k; });
     }
-    laplace_points<false>(g, nullptr, Q, [&](int p, double lap) {
-      if (is_interior_pt(p)) lap *= geo_ld(g, p, G_RSPHEREMP);  // rspheremp of the DSS that follows
-      if (valid) qtb[p * NLEV] = lap;
-    });
+    if (BIH)
+      laplace_points<false>(g, nullptr, Q, [&](int p, double lap) {
+        if (is_interior_pt(p)) lap *= geo_ld(g, p, G_RSPHEREMP);  // rspheremp of the DSS that follows
+        if (valid) qtb[p * NLEV] = lap;
+      });
   }
   cp_async_wait<0>();
 }
@@ -545,22 +551,18 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   PROBE(K_EULER_QMINMAX);
   {
     constexpr size_t smem_mm = 2 * (size_t)NPSQ * TPB * sizeof(double);
-    constexpr size_t smem_bih = 5 * (size_t)NPSQ * TPB * sizeof(double);
-    static bool attr_mm = false;
-    if (!attr_mm) {
-      CUDA_OK(cudaFuncSetAttribute(euler_qminmax_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bih));
-      attr_mm = true;
+    static bool attr_bih = false;
+    if (!attr_bih) {
+      CUDA_OK(cudaFuncSetAttribute(euler_qminmax_bih_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   bih_smem_doubles * (int)sizeof(double)));
+      CUDA_OK(cudaFuncSetAttribute(euler_qminmax_bih_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   bih_smem_doubles * (int)sizeof(double)));
+      attr_bih = true;
     }
-    if (mode == 2) {
-      static bool attr_bih = false;
-      if (!attr_bih) {
-        CUDA_OK(cudaFuncSetAttribute(euler_qminmax_bih_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     bih_smem_doubles * (int)sizeof(double)));
-        attr_bih = true;
-      }
-      euler_qminmax_bih_kernel<<<(int)(((long long)S.nelemd * NLEV + 31) / 32), BIH_T, bih_smem_doubles * sizeof(double),
-                                 S.stream>>>(a);
-    } else euler_qminmax_kernel<false><<<grid, TPB, smem_mm, S.stream>>>(a);
+    const int nb32 = (int)(((long long)S.nelemd * NLEV + 31) / 32);
+    if (mode == 2) euler_qminmax_bih_kernel<true><<<nb32, BIH_T, bih_smem_doubles * sizeof(double), S.stream>>>(a);
+    else if (HXX_QMM_SHARED) euler_qminmax_bih_kernel<false><<<nb32, BIH_T, bih_smem_doubles * sizeof(double), S.stream>>>(a);
+    else euler_qminmax_kernel<false><<<grid, TPB, smem_mm, S.stream>>>(a);
   }
   KERNEL_LAUNCHED(K_EULER_QMINMAX);
   if (mode == 0) {
