@@ -315,7 +315,7 @@ def main():
                 "algorithmic_bytes_per_launch": adv_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": nl.value,
                 "kernel_share_of_step": k_ms / ms if ms > 0 else None,
                 # the kernel's second ceiling (FP64 is uncontracted, --fmad=false): pipe utilisation of its three
-                # stages from the committed ncu capture (profiles/r1z_ncu_summary.txt)
+                # stages from the committed ncu capture (profiles/r1f_ncu_summary.txt)
                 "fp64_pipe_pct_ncu": fp64_pct}
     step_bytes = step_bytes_per_elem_step(cfg)
     step_gbs = value / n_gpus * step_bytes / 1e9
