@@ -1,15 +1,15 @@
 // Tracer advection — replaces EulerStepFunctor{,Impl}.hpp of the reference: one stage of the
 // 3-stage SSP-RK2 scheme per euler_step() call (EulerStepFunctorImpl.hpp:514-561).
 //
-// One thread per (element, level) walks a chunk of tracers; the level's 4x4 plane is in
-// registers, so the divergence, the weak Laplacians, the per-level min/max AND the
-// quasi-monotone limiter (whose reductions run over the 16 points of one level) are all
-// thread-local — no team reductions, no shared-memory exchange. The reference's per-element
-// set-up kernels (compute_dp :406-434, compute_2d_advection_step :585-626) are recomputed in
-// registers by each tracer chunk instead of round-tripping vstar/dpdissk/dp_star through HBM,
-// and the second biharmonic Laplacian (:216-231) is applied on the fly by the advection kernel.
+// One thread per (element, level) holds the level's 4x4 plane in registers, so the divergence, the weak
+// Laplacians, the per-level min/max AND the quasi-monotone limiter (whose reductions run over the 16
+// points of one level) are all thread-local — no team reductions. A block is 32 (element, level)
+// lanes x 4 warps: the per-level constants of the reference's per-element set-up kernels (compute_dp
+// :406-434, compute_2d_advection_step :585-626) are built once per block in shared memory instead of
+// round-tripping vstar/dpdissk/dp_star through HBM, and the warps split the tracers.
 // Algorithmic HBM traffic per (element, tracer, stage): min/max pass 1 tile read; advection
-// 1 read + 1 write (+1 read +1 write of qtens_biharmonic on the stage with hyperviscosity).
+// 1 read + 1 write; on the stage with hyperviscosity +1 write (first Laplacian), +1 read +1 write
+// (second Laplacian, in place), +1 read (the advection kernel adds the prepared term).
 #include "hxx.cuh"
 
 HXX_DEFINE_CONSTANTS()
@@ -56,105 +56,13 @@ __global__ void __launch_bounds__(TPB, 2)
   plane_store(divdp_proj + off_f(ie) + k, div);
 }
 
-// compute_dp + compute_qmin_qmax (:406-485) and, on the hyperviscosity stage,
+// compute_dp + compute_qmin_qmax (:406-485) and, on the hyperviscosity stage (BIH),
 // compute_biharmonic_pre (:196-214, dpdiss_adjustment :251-267): Q -> laplace(Q * dpdiss_ave / dp0).
-// The tracer planes are staged two tracers ahead with cp.async, as in the advection kernel.
-template <bool BIH>
-__global__ void __launch_bounds__(TPB, BIH ? 2 : 4) euler_qminmax_kernel(const EulerArgs a) {
-  extern __shared__ double s_all[];
-  __shared__ double s_geo[BIH ? geo_span(TPB) * NPSQ * GEO_N : 1];
-  const int e_first = (int)(((long long)blockIdx.x * TPB) / NLEV);
-  if (BIH) stage_geo<geo_span(TPB), TPB>(s_geo, a.geo, e_first, a.nelem);
-  int ie, k;
-  if (!map_thread(a.nelem, ie, k)) return;
-  double* const s_q = s_all + threadIdx.x;  // [2][16][TPB]
-  const GeoShared g{s_geo + (BIH ? (ie - e_first) * NPSQ * GEO_N : 0)};
-  const int q0 = blockIdx.y * a.qchunk, q1 = min(a.qsize, q0 + a.qchunk);
-  const double* const qin = a.qdp + off_q(ie, a.n0_qdp, 0) + k;
-  auto prefetch = [&](int q, int buf) {
-    if (q < q1) {
-      const double* src = qin + (size_t)q * NLF;
-      HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) cp_async8(s_q + (buf * NPSQ + p) * TPB, src + p * NLEV);
-    }
-    cp_async_commit();
-  };
-  prefetch(q0, 0);
-  prefetch(q0 + 1, 1);
-  // dp of compute_dp, its reciprocal and (hyperviscosity stage) dpdiss_ave are the same for every
-  // tracer: the BIH instantiation parks them in per-thread shared-memory slots [32 + 16][TPB] behind
-  // the staging buffers so that its Laplacian has the registers, the other one keeps them in registers
-  double* const s_dp = s_q + 2 * NPSQ * TPB;
-  double* const s_rdp = s_dp + NPSQ * TPB;
-  double* const s_dave = s_rdp + NPSQ * TPB;
-  double dps[BIH ? 1 : NPSQ];
-  const bool scale = BIH && a.nu_p > 0;
-  {
-    double r0[NPSQ], r1[NPSQ];
-    plane_load(a.derived_dp + off_f(ie) + k, r0);
-    plane_load(a.divdp_proj + off_f(ie) + k, r1);
-    HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) {
-      const double d = r0[p] - a.rhsmdt * r1[p];
-      if constexpr (BIH) { s_dp[p * TPB] = d; s_rdp[p * TPB] = 1.0 / d; }
-      else dps[p] = d;
-    }
-    if (scale) {
-      plane_load(a.dpdiss_ave + off_f(ie) + k, r0);
-      HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p) s_dave[p * TPB] = r0[p];
-    }
-  }
-  const double dp0k = dc.dp0[k], rdp0k = 1.0 / dp0k;
-  double* ql = a.qlim + ((size_t)ie * QSIZE_D + q0) * 2 * NLEV + k;
-  double* qtb = a.qtens_biharmonic + ((size_t)ie * QSIZE_D + q0) * NLF + k;
-  double mn_n = 0.0, mx_n = 0.0;
-  if (a.rhs_mode == 1) { mn_n = ql[0]; mx_n = ql[NLEV]; }
-  for (int q = q0; q < q1; ++q, ql += 2 * NLEV, qtb += NLF) {
-    const int buf = (q - q0) & 1;
-    double mn = mn_n, mx = mx_n;
-    if (a.rhs_mode == 1 && q + 1 < q1) { mn_n = ql[2 * NLEV]; mx_n = ql[3 * NLEV]; }
-    cp_async_wait<1>();
-    double Q[NPSQ];
-    HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) Q[p] = s_q[(buf * NPSQ + p) * TPB];
-    prefetch(q + 2, buf);
-    HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) {
-      if constexpr (BIH) Q[p] = div_rcp(Q[p], s_dp[p * TPB], s_rdp[p * TPB]);
-      else Q[p] = Q[p] / dps[p];
-    }
-    if (a.rhs_mode != 1) { mn = Q[0]; mx = Q[0]; }
-    HXX_UNROLL
-    for (int p = 0; p < NPSQ; ++p) { mn = fmin(mn, Q[p]); mx = fmax(mx, Q[p]); }
-    ql[0] = mn;
-    ql[NLEV] = mx;
-    if (BIH) {
-      double lap[NPSQ];
-      if (scale) {
-        HXX_UNROLL
-        for (int p = 0; p < NPSQ; ++p) Q[p] = div_rcp(Q[p] * s_dave[p * TPB], dp0k, rdp0k);
-      }
-      laplace_simple(g, Q, lap);
-      HXX_UNROLL
-      for (int p = 0; p < NPSQ; ++p)
-        if (is_interior_pt(p)) lap[p] *= geo_ld(g, p, G_RSPHEREMP);  // rspheremp of the DSS that follows
-      plane_store(qtb, lap);
-    }
-  }
-  cp_async_wait<0>();
-}
-
-// The hyperviscosity stage's min/max pass (compute_dp + compute_qmin_qmax + compute_biharmonic_pre) in the
-// block shape of the advection kernel below: 32 (element, level) lanes x BIH_NW warps that share dp, its
+// Block shape of the advection kernel below: 32 (element, level) lanes x BIH_NW warps that share dp, its
 // reciprocal and dpdiss_ave in shared memory and split the tracers; each warp stages its tracers'
 // planes two ahead with cp.async. The Laplacian is finished point by point (laplace_points).
 #ifndef HXX_BIH_NW
 #define HXX_BIH_NW 4
-#endif
-// 1: stages 1 and 2 use the same block shape (reciprocal division); 0: the thread-local kernel above
-#ifndef HXX_QMM_SHARED
-#define HXX_QMM_SHARED 1
 #endif
 #ifndef HXX_BIH_MINB
 #define HXX_BIH_MINB 4
@@ -163,7 +71,7 @@ constexpr int BIH_NW = HXX_BIH_NW;
 constexpr int BIH_T = 32 * BIH_NW;
 constexpr int bih_smem_doubles = 3 * NPSQ * 32 + BIH_NW * 2 * NPSQ * 32;
 template <bool BIH>
-__global__ void __launch_bounds__(BIH_T, HXX_BIH_MINB) euler_qminmax_bih_kernel(const EulerArgs a) {
+__global__ void __launch_bounds__(BIH_T, HXX_BIH_MINB) euler_qminmax_kernel(const EulerArgs a) {
   extern __shared__ double s_all[];
   __shared__ double s_geo[geo_span(32) * NPSQ * GEO_N];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -550,19 +458,17 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   const dim3 grid(nblocks_flat(S.nelemd), (nq + a.qchunk - 1) / a.qchunk);
   PROBE(K_EULER_QMINMAX);
   {
-    constexpr size_t smem_mm = 2 * (size_t)NPSQ * TPB * sizeof(double);
     static bool attr_bih = false;
     if (!attr_bih) {
-      CUDA_OK(cudaFuncSetAttribute(euler_qminmax_bih_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CUDA_OK(cudaFuncSetAttribute(euler_qminmax_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    bih_smem_doubles * (int)sizeof(double)));
-      CUDA_OK(cudaFuncSetAttribute(euler_qminmax_bih_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CUDA_OK(cudaFuncSetAttribute(euler_qminmax_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    bih_smem_doubles * (int)sizeof(double)));
       attr_bih = true;
     }
     const int nb32 = (int)(((long long)S.nelemd * NLEV + 31) / 32);
-    if (mode == 2) euler_qminmax_bih_kernel<true><<<nb32, BIH_T, bih_smem_doubles * sizeof(double), S.stream>>>(a);
-    else if (HXX_QMM_SHARED) euler_qminmax_bih_kernel<false><<<nb32, BIH_T, bih_smem_doubles * sizeof(double), S.stream>>>(a);
-    else euler_qminmax_kernel<false><<<grid, TPB, smem_mm, S.stream>>>(a);
+    if (mode == 2) euler_qminmax_kernel<true><<<nb32, BIH_T, bih_smem_doubles * sizeof(double), S.stream>>>(a);
+    else euler_qminmax_kernel<false><<<nb32, BIH_T, bih_smem_doubles * sizeof(double), S.stream>>>(a);
   }
   KERNEL_LAUNCHED(K_EULER_QMINMAX);
   if (mode == 0) {
