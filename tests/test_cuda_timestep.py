@@ -122,6 +122,9 @@ CASES = {
     # rsplit = 0: Eulerian vertical advection in CAAR, tracer-only remap (test-list.cmake's r0 variants)
     "ne4-r0": dict(base="ne4", rsplit=0),
     "prtcA-r0-moist-q3": dict(base="prtcA", rsplit=0, moisture=1, qsplit=3),
+    # no tracers at all (the remap then carries only the three state fields; forcing and update_q have nothing to do)
+    "prtcA-q0": dict(base="prtcA", qsize=0),
+    "ne4-r0-q0": dict(base="ne4", rsplit=0, qsize=0),
 }
 
 
