@@ -1,11 +1,14 @@
 // CAAR — compute_and_apply_rhs, one Runge-Kutta stage of the dynamics. Replaces
-// CaarFunctor.{hpp,cpp} / CaarFunctorImpl.hpp of the reference (rsplit > 0 path) plus the small
+// CaarFunctor.{hpp,cpp} / CaarFunctorImpl.hpp of the reference (rsplit > 0, and rsplit = 0 as the VADV
+// instantiation) plus the small
 // element-wise kernels of prim_driver.cpp / prim_step.cpp / prim_advance_exp.cpp.
 //
 // One thread per (element, level); the 4x4 plane of the level lives in registers, every
 // horizontal operator is thread-local. The three vertical integrals (pressure, hydrostatic
 // geopotential, omega) run in the reference's sequential order through shared memory
 // (non-CUDA branches CaarFunctorImpl.hpp:621-650, :689-729, :854-889), one thread per column.
+// Planes that outlive a phase (pressure, phi, omega, Tv, the energy gradient) wait in per-thread
+// shared-memory slots and the operators finish one point at a time, so nothing spills to local memory.
 // Algorithmic HBM traffic per element and stage: read v,T,dp3d at n0 and nm1 (8 tiles, 4 when
 // nm1 == n0), write 4 tiles, plus read-modify-write of derived_vn0 (2) and omega_p (1) when
 // eta_ave_w != 0.

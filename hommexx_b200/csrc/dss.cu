@@ -33,6 +33,12 @@ static const int CORNER_PTS[4] = {0, 3, 12, 15};
 constexpr int NODES_PB = (NLEV * 4 <= 288) ? 4 : 2;  // nodes per block
 constexpr int DSS_FPB = 8;                           // fields per thread (grid.y chunks)
 
+#ifndef HXX_DSS_PAIR_UB
+#define HXX_DSS_PAIR_UB 4
+#endif
+#ifndef HXX_DSS_QUAD_UB
+#define HXX_DSS_QUAD_UB 2
+#endif
 #ifndef HXX_DSS_FB
 #define HXX_DSS_FB 1
 #endif
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(DSS_TPB)
     rb = __ldg(geo + (size_t)pr.b * GEO_N + G_RSPHEREMP);
   }
   const int f0 = blockIdx.y * DSS_FPB, f1 = min(fl.nf, f0 + DSS_FPB);
-  constexpr int UB = 4;  // fields whose loads are issued before the first store
+  constexpr int UB = HXX_DSS_PAIR_UB;  // fields whose loads are issued before the first store
   for (int fb = f0; fb < f1; fb += UB) {
     double *pa[UB], *pb[UB];
     double va[UB], vb[UB], qa[UB], qb[UB];
@@ -188,7 +194,7 @@ __global__ void __launch_bounds__(DSS_TPB)
   }
   const bool s1 = qd.swaps & 1, s2 = qd.swaps & 2, s3 = qd.swaps & 4;
   const int f0 = blockIdx.y * DSS_FPB, f1 = min(fl.nf, f0 + DSS_FPB);
-  constexpr int UB = 2;
+  constexpr int UB = HXX_DSS_QUAD_UB;
   for (int fb = f0; fb < f1; fb += UB) {
     double* ptr[UB][4];
     double v[UB][4], qa[UB][4];

@@ -2,7 +2,9 @@
 // hypervis_subcycle x [ first weak Laplacian (TagFirstLaplaceHV, .hpp:72-87) -> DSS*rspheremp ->
 // second Laplacian (TagSecondLaplaceConstHV/TensorHV :92-131) fused with TagHyperPreExchange
 // (:161-257) -> DSS -> TagUpdateStates (:134-158) ].
-// One thread per (element, level), the level's 4x4 planes in registers, no shared memory.
+// One thread per (element, level), the level's 4x4 planes in registers; operators are finished one point
+// at a time (hxx_sphere.cuh), the block's geometry / metinv records and the vector Laplacian's parked
+// weak gradient live in shared memory.
 #include <type_traits>
 
 #include "hxx.cuh"
