@@ -157,8 +157,17 @@ __device__ __forceinline__ void ppm_sweep(const ColData& c, int alg, bool active
     const double am = A0;
     double al = AI0, ar = AI1;
     if ((ar - am) * (am - al) <= 0.) { al = am; ar = am; }
-    if ((ar - al) * (am - (al + ar) / 2.0) > div_rcp((ar - al) * (ar - al), 6.0, r6)) al = 3.0 * am - 2.0 * ar;
-    if ((ar - al) * (am - (al + ar) / 2.0) < -div_rcp((ar - al) * (ar - al), 6.0, r6)) ar = 3.0 * am - 2.0 * al;
+    {
+      // the two overshoot tests of :488-497 share their operands unless the first one fires
+      double lhs = (ar - al) * (am - (al + ar) / 2.0);
+      double lim = div_rcp((ar - al) * (ar - al), 6.0, r6);
+      if (lhs > lim) {
+        al = 3.0 * am - 2.0 * ar;
+        lhs = (ar - al) * (am - (al + ar) / 2.0);
+        lim = div_rcp((ar - al) * (ar - al), 6.0, r6);
+      }
+      if (lhs < -lim) ar = 3.0 * am - 2.0 * al;
+    }
     double c0 = 1.5 * am - (al + ar) / 4.0, c1 = ar - al, c2 = 3.0 * (-2.0 * am + (al + ar));
     if (alg == 2 && (cc < 2 || cc >= NLEV - 2)) {  // PpmFixedParabola::apply_ppm_boundary :110-133
       c0 = am; c1 = 0.0; c2 = 0.0;
