@@ -379,6 +379,48 @@ void build_geometry(HommeDriver& h) {
           const size_t o = ((size_t)l * 4 + c * 2 + r) * NPSQ + pt;
           h.D[o] = Dmath[r][c]; h.Dinv[o] = Dimath[r][c]; h.metinv[o] = Mimath[r][c];
         }
+      if (h.p.hypervis_scaling != 0.0) {
+        // tensor hyperviscosity V = (DE) (Lam*)^2 Lam (DE)^T from the eigen-decomposition of metinv
+        // (cube_mod.F90:315-428); maxloc scans column-major, first maximum wins
+        const double (&M)[2][2] = Mimath;
+        const double disc = std::sqrt(4.0 * M[0][1] * M[1][0] + (M[0][0] - M[1][1]) * (M[0][0] - M[1][1]));
+        const double eig[2] = {(M[0][0] + M[1][1] + disc) / 2.0, (M[0][0] + M[1][1] - disc) / 2.0};
+        double DE[2][2] = {{M[0][0] - eig[0], M[0][1]}, {M[1][0], M[1][1] - eig[0]}};
+        int ir = 0, ic = 0;
+        double mx = -1.0;
+        for (int c = 0; c < 2; ++c)
+          for (int r = 0; r < 2; ++r)
+            if (std::fabs(DE[r][c]) > mx) { mx = std::fabs(DE[r][c]); ir = r; ic = c; }
+        double E[2][2];
+        if (mx == 0.0) { E[0][0] = 1; E[1][0] = 0; }
+        else if (ir == 0 && ic == 0) { E[1][0] = 1; E[0][0] = -DE[1][0] / DE[0][0]; }
+        else if (ir == 0 && ic == 1) { E[1][0] = 1; E[0][0] = -DE[1][1] / DE[0][1]; }
+        else if (ir == 1 && ic == 0) { E[0][0] = 1; E[1][0] = -DE[0][0] / DE[1][0]; }
+        else { E[0][0] = 1; E[1][0] = -DE[0][1] / DE[1][1]; }
+        E[0][1] = -E[1][0];
+        E[1][1] = E[0][0];
+        for (int c = 0; c < 2; ++c) {
+          const double nrm = std::sqrt(E[0][c] * E[0][c] + E[1][c] * E[1][c]);
+          E[0][c] /= nrm; E[1][c] /= nrm;
+        }
+        for (int r = 0; r < 2; ++r)
+          for (int c = 0; c < 2; ++c) DE[r][c] = Dmath[r][0] * E[0][c] + Dmath[r][1] * E[1][c];
+        const double rearth = 6.376e6;
+        double DEL[2][2];
+        for (int c = 0; c < 2; ++c) {
+          const double lamStar = 1.0 / std::pow(eig[c], h.p.hypervis_scaling / 4.0) * (rearth * rearth);
+          for (int r = 0; r < 2; ++r) DEL[r][c] = (lamStar * lamStar) * eig[c] * DE[r][c];
+        }
+        for (int r = 0; r < 2; ++r)
+          for (int c = 0; c < 2; ++c)
+            h.tensorvisc[((size_t)l * 4 + c * 2 + r) * NPSQ + pt] = DEL[r][0] * DE[c][0] + DEL[r][1] * DE[c][1];
+        // vec_sphere2cart (cube_mod.F90:172-178), F90 (np,np,3,2): memory [dir][comp][pt]
+        const double la = h.lat[(size_t)l * NPSQ + pt], lo = h.lon[(size_t)l * NPSQ + pt];
+        const double vs[2][3] = {{-std::sin(lo), std::cos(lo), 0.0},
+                                 {-std::sin(la) * std::cos(lo), -std::sin(la) * std::sin(lo), std::cos(la)}};
+        for (int d = 0; d < 2; ++d)
+          for (int c3 = 0; c3 < 3; ++c3) h.vec_sph2cart[((size_t)l * 6 + d * 3 + c3) * NPSQ + pt] = vs[d][c3];
+      }
       const size_t s = (size_t)l * NPSQ + pt;
       const double w = (double)(h.gll.w[pt / NP] * h.gll.w[pt % NP]);
       h.mp[s] = w;
@@ -698,6 +740,7 @@ double* hd_array(HommeDriver* h, const char* name, int64_t* n) {
   else if (s == "T") a = &h->T; else if (s == "dp3d") a = &h->dp3d; else if (s == "Qdp") a = &h->Qdp;
   else if (s == "Q") a = &h->Q; else if (s == "ps_v") a = &h->ps_v; else if (s == "omega_p") a = &h->omega_p;
   else if (s == "lat") a = &h->lat; else if (s == "lon") a = &h->lon; else if (s == "gid") a = &h->gidf;
+  else if (s == "tensorvisc") a = &h->tensorvisc; else if (s == "vec_sph2cart") a = &h->vec_sph2cart;
   else if (s == "FM") a = &h->FM; else if (s == "FT") a = &h->FT; else if (s == "FQ") a = &h->FQ;
   else if (s == "Qvar") a = &h->accum[0]; else if (s == "Qmass") a = &h->accum[1]; else if (s == "Q1mass") a = &h->accum[2];
   else if (s == "IEner") a = &h->accum[3]; else if (s == "IEner_wet") a = &h->accum[4];

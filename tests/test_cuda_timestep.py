@@ -122,6 +122,11 @@ CASES = {
     # rsplit = 0: Eulerian vertical advection in CAAR, tracer-only remap (test-list.cmake's r0 variants)
     "ne4-r0": dict(base="ne4", rsplit=0),
     "prtcA-r0-moist-q3": dict(base="prtcA", rsplit=0, moisture=1, qsplit=3),
+    # tensor hyperviscosity (prtcB-r3-tensorhv-dry.nl: hypervis_scaling 3.2, nu 1e-9, hypervis_subcycle 2), with the
+    # driver's tensorVisc / vec_sphere2cart (cube_mod.F90:172-178,315-428)
+    "prtcA-tensorhv": dict(base="prtcA", hypervis_scaling=3.2, nu=1e-9, nu_p=1e-9, nu_q=1e-9, nu_s=1e-9, nu_div=1e-9,
+                           hypervis_subcycle=2),
+    "ne4-tensorhv-nudiv": dict(base="ne4", hypervis_scaling=3.2, nu=5e-8, nu_p=5e-8, nu_q=5e-8, nu_s=5e-8, nu_div=1.25e-7),
     # no tracers at all (the remap then carries only the three state fields; forcing and update_q have nothing to do)
     "prtcA-q0": dict(base="prtcA", qsize=0),
     "ne4-r0-q0": dict(base="ne4", rsplit=0, qsize=0),
