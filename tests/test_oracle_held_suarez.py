@@ -1,0 +1,58 @@
+"""Held-Suarez forcing harness (hommexx_b200/held_suarez.py; reference physics/heldsuarez/held_suarez_mod.F90)
+driving the oracle through f90_push_forcing_to_cxx + prim_run_subcycle_c (ftype = 0)."""
+import numpy as np
+
+from hommexx_b200 import held_suarez as hs
+from hommexx_b200 import homme
+
+
+def test_forcing_formulas():
+    hyai, hybi, hyam, hybm = homme.read_vcoord(26)
+    lat = np.linspace(-1.5, 1.5, 32).reshape(2, 4, 4)
+    ps = np.full((2, 4, 4), 1.0e5)
+    T = np.full((2, 26, 4, 4), 250.0)
+    ft, Teq = hs.hs_T_forcing(hyam, hybm, ps, T, lat)
+    assert Teq.min() >= 200.0 and Teq.max() <= 315.0 + 1e-9
+    # equilibrium temperature: warmest at the equatorial surface, 200 K floor aloft
+    assert Teq[:, -1].max() > 300.0 and np.isclose(Teq[:, 0].min(), 200.0)
+    # relaxation pulls towards Teq at rate between k_a and k_s
+    rate = -ft / (T - Teq)
+    assert rate.min() >= hs.K_A * (1 - 1e-12) and rate.max() <= hs.K_S * (1 + 1e-12)
+    v = np.ones((2, 26, 2, 4, 4))
+    fm = hs.hs_v_forcing(hyam, hybm, v)
+    sigma = hyam + hybm
+    assert (fm[:, sigma <= hs.SIGMA_B] == 0).all()                   # free atmosphere: no friction
+    assert np.isclose(fm[:, -1].min(), -hs.K_F * (sigma[-1] - 0.7) / 0.3)
+
+
+def test_held_suarez_forced_run_on_the_oracle():
+    cfg = homme.preset("prtcA", qsize=0, ftype=0)
+    runs = {}
+    for forced in (False, True):
+        h = homme.Homme(cfg, homme.ORACLE_LIB)
+        h.init_dycore()
+        for _ in range(6):
+            if forced:
+                hs.forced_step(h)
+            else:
+                h.run_subcycle()
+        h.push_results()
+        n0 = h.time_levels()[2] - 1
+        runs[forced] = {k: v[:, n0].copy() for k, v in h.state().items() if k in ("T", "v", "ps_v")}
+        lat = h.array("lat").reshape(h.nelemd, 4, 4).copy()
+        vc = h.vcoord
+        h.close()
+    f, u = runs[True], runs[False]
+    assert all(np.isfinite(a).all() for a in f.values())
+    assert not np.array_equal(f["T"], u["T"])
+    # Rayleigh friction: the boundary-layer winds are weaker than in the unforced run, the free atmosphere barely moves
+    sigma = vc[2] + vc[3]
+    bl = sigma > 0.85
+    ke = lambda a, m: (a[:, m] ** 2).sum()
+    assert ke(f["v"], bl) < 0.97 * ke(u["v"], bl)
+    assert abs(ke(f["v"], ~bl) / ke(u["v"], ~bl) - 1.0) < 0.05
+    # Newtonian cooling: T moved towards Teq where it was far from it (6 calls = 3 h at k_T <= 1/4 day^-1)
+    _, Teq = hs.hs_T_forcing(vc[2], vc[3], u["ps_v"], u["T"], lat)
+    far = np.abs(u["T"] - Teq) > 20.0
+    assert far.any()
+    assert (np.abs(f["T"] - Teq)[far]).mean() < (np.abs(u["T"] - Teq)[far]).mean()
