@@ -83,3 +83,56 @@ def test_two_gpu_run_is_bit_identical_to_single_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "bit-identical" in r.stdout
+
+
+@pytest.mark.parametrize("ne,npart", [(6, 8), (10, 4), (7, 3)])
+def test_partition_properties_many_parts(ne, npart):
+    """The SFC partition the 4- and 8-GPU runs use, checked in one process: every element owned once, sizes as
+    genspacepart (spacecurve_mod.F90:1232-1264), parts spatially compact (at most two edge-connected patches and a
+    perimeter-sized halo), and every off-rank connection mirrored by the owner."""
+    from hommexx_b200 import homme
+    parts = []
+    for r in range(npart):
+        cfg = homme.preset("ne4", ne=ne, npart=npart)
+        cfg.part_id = r
+        h = homme.Homme(cfg, homme.ORACLE_LIB)
+        parts.append((h.local_gids(), h.connections(), float(h.array("spheremp").sum())))
+        nelem = h.nelem
+        h.close()
+    allg = np.concatenate([g for g, _, _ in parts])
+    assert sorted(allg.tolist()) == list(range(nelem))
+    base, extra = divmod(nelem, npart)
+    assert [len(g) for g, _, _ in parts] == [base + (1 if r < extra else 0) for r in range(npart)]
+    assert abs(sum(s for _, _, s in parts) - 4 * np.pi) < 1e-9
+    mirror, halo = {}, []
+    for r, (gids, conn, _) in enumerate(parts):
+        mine = set((gids + 1).tolist())
+        # edge-connected patch: flood fill over on-rank EDGE connections (pos 1..4) reaches every element
+        adj = {g: set() for g in mine}
+        off = 0
+        for t in conn:
+            assert t[3] == r + 1
+            if t[7] == r + 1:
+                if t[2] <= 4:
+                    adj[t[1]].add(t[5])
+            else:
+                off += 1
+                mirror[(r + 1, t[1], t[2])] = (t[7], t[5], t[6])
+        left, patches = set(mine), 0
+        while left:
+            patches += 1
+            todo = [next(iter(left))]
+            while todo:
+                g = todo.pop()
+                if g not in left:
+                    continue
+                left.discard(g)
+                todo.extend(adj[g] & left)
+        # the per-face curves are joined end to start, which is not always an element adjacency: a part
+        # that spans a face change may be two patches, never more
+        assert patches <= 2, f"part {r} is scattered over {patches} patches"
+        halo.append(off)
+    for (pid, gid, pos), (rpid, rgid, rpos) in mirror.items():
+        assert mirror.get((rpid, rgid, rpos)) == (pid, gid, pos)
+    # compactness: the halo of a part is a perimeter, far below its 8 * size connections
+    assert max(halo) < 0.75 * 8 * (base + 1)
