@@ -101,6 +101,15 @@ def preset(name: str, **over) -> Config:
 
 
 def read_vcoord(nlev: int, name: str = ""):
+    if name == "dcmip-z12km":
+        # DCMIP 2012 test 1-x grid (dcmip_tests.F90:62-68): nlev layers evenly spaced in z up to 12 km in an
+        # isothermal 300 K atmosphere, eta = exp(-z/H); hybrid coefficients with p(eta, ps = p0) = p0 eta
+        H = 287.04 * 300.0 / 9.80616
+        etai = np.exp(-np.linspace(12000.0, 0.0, nlev + 1) / H)
+        hybi = (etai - etai[0]) / (1.0 - etai[0])
+        hyai = etai - hybi
+        hyam, hybm = 0.5 * (hyai[1:] + hyai[:-1]), 0.5 * (hybi[1:] + hybi[:-1])
+        return hyai, hybi, hyam, hybm
     if not name:
         name = {72: "acme-72", 26: "cam-26"}.get(nlev, "")
     if name:
