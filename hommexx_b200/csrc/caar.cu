@@ -367,11 +367,9 @@ void caar_run(int nm1, int n0, int np1, double dt, double eta_ave_w, int n0_qdp,
              dt, eta_ave_w, with_dss ? 1 : 0, S.store_phi ? 1 : 0};
   constexpr size_t plane = (size_t)CAAR_E * NPSQ * (NLEV + 1) * sizeof(double);
   constexpr size_t smem = 5 * plane, smem_vadv = 9 * plane;
-  static bool attr = false;
-  if (!attr) {
+  if (HXX_ONCE_PER_SESSION()) {
     CUDA_OK(cudaFuncSetAttribute(caar_kernel<CAAR_E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaFuncSetAttribute(caar_kernel<CAAR_E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_vadv));
-    attr = true;
   }
   const int nb = (S.nelemd + CAAR_E - 1) / CAAR_E;
   PROBE(K_CAAR);

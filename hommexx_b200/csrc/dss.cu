@@ -304,7 +304,10 @@ void free_exchange_plan() {
   if (S.sendbuf) { cudaFree(S.sendbuf); S.sendbuf = nullptr; }
   if (S.recvbuf) { cudaFree(S.recvbuf); S.recvbuf = nullptr; }
   S.nnodes = 0; S.n_halo_pts = S.n_send_pts = S.n_halo_conn = S.n_send_conn = 0;
+  // every per-peer table: build_exchange_plan() appends, and halo_sendrecv() indexes them by peer slot
   S.peer.clear();
+  S.peer_send_off.clear(); S.peer_send_cnt.clear(); S.peer_recv_off.clear(); S.peer_recv_cnt.clear();
+  S.peer_csend_off.clear(); S.peer_csend_cnt.clear(); S.peer_crecv_off.clear(); S.peer_crecv_cnt.clear();
 }
 
 void build_exchange_plan() {
@@ -549,12 +552,14 @@ static void halo_sendrecv(const std::vector<int>& soff, const std::vector<int>& 
 #ifdef HXX_WITH_NCCL
   ncclComm_t comm = (ncclComm_t)S.nccl;
   if (!comm) runtime_abort("halo exchange: NCCL communicator not initialised", 13);
-  ncclGroupStart();
+  bool ok = ncclGroupStart() == ncclSuccess;
   for (size_t i = 0; i < S.peer.size(); ++i) {
-    ncclSend(S.sendbuf + (size_t)soff[i] * unit, (size_t)scnt[i] * unit, ncclDouble, S.peer[i], comm, S.comm_stream);
-    ncclRecv(S.recvbuf + (size_t)roff[i] * unit, (size_t)rcnt[i] * unit, ncclDouble, S.peer[i], comm, S.comm_stream);
+    ok = ok && ncclSend(S.sendbuf + (size_t)soff[i] * unit, (size_t)scnt[i] * unit, ncclDouble, S.peer[i], comm,
+                        S.comm_stream) == ncclSuccess;
+    ok = ok && ncclRecv(S.recvbuf + (size_t)roff[i] * unit, (size_t)rcnt[i] * unit, ncclDouble, S.peer[i], comm,
+                        S.comm_stream) == ncclSuccess;
   }
-  if (ncclGroupEnd() != ncclSuccess) runtime_abort("halo exchange: ncclGroupEnd failed", 1);
+  if (ncclGroupEnd() != ncclSuccess || !ok) runtime_abort("halo exchange: NCCL send/recv failed", 1);
 #else
   (void)soff; (void)scnt; (void)roff; (void)rcnt; (void)unit;
   runtime_abort("halo exchange: built without NCCL", 12);
@@ -600,6 +605,17 @@ void dss_exchange(const FieldList& fl, bool rspheremp) {
     HXX_DSS_LAUNCH(dss_nodes_kernel, grid, NODES_PB * NLEV, S.nodes, S.nnodes, fl, S.geo, S.recvbuf);
   }
 #undef HXX_DSS_LAUNCH
+}
+
+// Asynchronous NCCL errors (a peer that died) surface here instead of as a hang; polled once per
+// prim_run_subcycle_c, next to the remap's abort flag.
+void check_comm_errors() {
+#ifdef HXX_WITH_NCCL
+  if (!S.nccl) return;
+  ncclResult_t st = ncclSuccess;
+  if (ncclCommGetAsyncError((ncclComm_t)S.nccl, &st) != ncclSuccess || (st != ncclSuccess && st != ncclInProgress))
+    runtime_abort("halo exchange: asynchronous NCCL error (a peer rank failed?)", 1);
+#endif
 }
 
 void scale_interior_rspheremp(const FieldList& fl) {

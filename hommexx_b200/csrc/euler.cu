@@ -458,13 +458,11 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   const dim3 grid(nblocks_flat(S.nelemd), (nq + a.qchunk - 1) / a.qchunk);
   PROBE(K_EULER_QMINMAX);
   {
-    static bool attr_bih = false;
-    if (!attr_bih) {
+    if (HXX_ONCE_PER_SESSION()) {
       CUDA_OK(cudaFuncSetAttribute(euler_qminmax_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    bih_smem_doubles * (int)sizeof(double)));
       CUDA_OK(cudaFuncSetAttribute(euler_qminmax_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    bih_smem_doubles * (int)sizeof(double)));
-      attr_bih = true;
     }
     const int nb32 = (int)(((long long)S.nelemd * NLEV + 31) / 32);
     if (mode == 2) euler_qminmax_kernel<true><<<nb32, BIH_T, bih_smem_doubles * sizeof(double), S.stream>>>(a);
@@ -484,21 +482,17 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   const bool tavg = tavg_n0_qdp >= 0;
   const size_t smem = (size_t)(hv ? advect_smem_doubles<true>() : advect_smem_doubles<false>()) * sizeof(double);
   const int adv_blocks = (int)(((long long)S.nelemd * NLEV + 31) / 32);
-  static bool attr = false;
-  if (!attr) {
+  if (HXX_ONCE_PER_SESSION()) {
 #define HXX_ADV_ATTR(H, T)                                                                                  \
   CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                advect_smem_doubles<H>() * (int)sizeof(double)))
     HXX_ADV_ATTR(false, false); HXX_ADV_ATTR(false, true); HXX_ADV_ATTR(true, false); HXX_ADV_ATTR(true, true);
 #undef HXX_ADV_ATTR
-    attr = true;
   }
   if (hv && !HV_FUSED) {  // compute_biharmonic_post: the second Laplacian, in place
-    static bool attr_hp = false;
-    if (!attr_hp) {
+    if (HXX_ONCE_PER_SESSION()) {
       CUDA_OK(cudaFuncSetAttribute(euler_hvpost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    2 * NPSQ * TPB * (int)sizeof(double)));
-      attr_hp = true;
     }
     PROBE(K_EULER_QMINMAX);
     euler_hvpost_kernel<<<grid, TPB, 2 * (size_t)NPSQ * TPB * sizeof(double), S.stream>>>(a);

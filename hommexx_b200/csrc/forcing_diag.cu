@@ -173,15 +173,13 @@ void prim_diag_scalars(bool before_advance, int ivar) {
   push_Q_to_host(S.diag[0]);  // sync_to_host(tracers.Q, h_Q) :60-62
   if (!nq) return;
   const size_t cnt = (size_t)n * nq * NPSQ;
-  double* d = nullptr;
-  CUDA_OK(cudaMalloc(&d, cnt * 2 * sizeof(double)));
+  double* d = (double*)diag_scratch(cnt * 2 * sizeof(double));
   PROBE(K_DIAG);
   diag_scalars_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, S.stream>>>(S.qdp, S.Q, d, n, nq, t2_qdp);
   KERNEL_LAUNCHED(K_DIAG);
   g_host.resize(cnt * 2);
   CUDA_OK(cudaMemcpyAsync(g_host.data(), d, cnt * 2 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
   CUDA_OK(cudaStreamSynchronize(S.stream));
-  CUDA_OK(cudaFree(d));
   double *Qvar = S.diag[1], *Qmass = S.diag[2], *Q1mass = S.diag[3];  // [ie][4][QSIZE_D][16], [ie][QSIZE_D][16]
   for (int ie = 0; ie < n; ++ie)
     for (int q = 0; q < nq; ++q)
@@ -198,8 +196,7 @@ void prim_energy_halftimes(bool before_advance, int ivar) {
   if (!S.nelemd || !S.diag[4]) return;
   const int n = S.nelemd;
   const size_t cnt = (size_t)n * NPSQ;
-  double* d = nullptr;
-  CUDA_OK(cudaMalloc(&d, cnt * 4 * sizeof(double)));
+  double* d = (double*)diag_scratch(cnt * 4 * sizeof(double));
   PROBE(K_DIAG);
   diag_energy_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, S.stream>>>(S.v, S.t, S.ps_v, S.qdp, S.geo, d, n, t1, t1_qdp,
                                                                          S.p.use_cpstar ? 1 : 0);
@@ -207,7 +204,6 @@ void prim_energy_halftimes(bool before_advance, int ivar) {
   g_host.resize(cnt * 4);
   CUDA_OK(cudaMemcpyAsync(g_host.data(), d, cnt * 4 * sizeof(double), cudaMemcpyDeviceToHost, S.stream));
   CUDA_OK(cudaStreamSynchronize(S.stream));
-  CUDA_OK(cudaFree(d));
   double *IE = S.diag[4], *IEw = S.diag[5], *KE = S.diag[6], *PE = S.diag[7];  // [ie][4][16]; IEner_wet [ie][16]
   for (int ie = 0; ie < n; ++ie)
     for (int p = 0; p < NPSQ; ++p) {

@@ -283,14 +283,12 @@ void hypervis_run(int np1, double dt_in, double eta_ave_w) {
            p.nu_p, p.nu_top, p.nu_ratio1, p.nu_ratio2, p.hypervis_subcycle, p.consthv ? 1 : 0};
   const int nb = nblocks_flat(S.nelemd);
   constexpr size_t park_bytes = 2 * (size_t)NPSQ * TPB * sizeof(double);  // two parked planes per thread
-  static bool attr = false;
-  if (!attr) {  // static + dynamic shared memory passes 48 KB at small NLEV (more elements per block)
+  if (HXX_ONCE_PER_SESSION()) {  // static + dynamic shared memory passes 48 KB at small NLEV (more elements per block)
     const int pb = (int)park_bytes;
     CUDA_OK(cudaFuncSetAttribute(hv_first_laplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
     CUDA_OK(cudaFuncSetAttribute(hv_second_vector_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
     CUDA_OK(cudaFuncSetAttribute(hv_second_vector_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
     CUDA_OK(cudaFuncSetAttribute(hv_second_vector_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
-    attr = true;
   }
   for (int icycle = 0; icycle < p.hypervis_subcycle; ++icycle) {
     PROBE(K_HV_FIRST);

@@ -170,6 +170,11 @@ struct Session {
   double* diag[8] = {};
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  void* diag_scratch = nullptr;  // device sums of the diagnostics (grown on demand, kept for the session)
+  size_t diag_scratch_bytes = 0;
+  // Incremented by initialize_hommexx_session: per-function attributes (dynamic shared-memory limits) are
+  // per device/context, so every translation unit re-applies them when it sees a new session.
+  int session_id = 0;
 };
 
 extern Session S;
@@ -189,6 +194,15 @@ void probe_end(int id);
     CUDA_OK(cudaGetLastError());                                         \
     if (::hxx::S.profile_mask >> (id) & 1ull) ::hxx::probe_end(id);      \
   } while (0)
+
+// True the first time a call site is reached in each session (function attributes are per device / context).
+#define HXX_ONCE_PER_SESSION()                           \
+  ([] {                                                  \
+    static int seen = -1;                                \
+    if (seen == ::hxx::S.session_id) return false;       \
+    seen = ::hxx::S.session_id;                          \
+    return true;                                         \
+  }())
 
 // per-translation-unit constant bank (no relocatable device code: each TU owns a copy)
 void register_const_uploader(void (*fn)(const DevConst&));
@@ -273,6 +287,7 @@ void build_exchange_plan();
 void free_exchange_plan();
 void dss_exchange(const FieldList& fl, bool rspheremp);  // boundary nodes only (interior folded by producer unless told)
 void scale_interior_rspheremp(const FieldList& fl);      // the 4 interior points * rspheremp
+void check_comm_errors();
 void minmax_exchange();                                  // qlim -> qlim (neighbourhood min/max)
 FieldList fields_caar(int tl);
 FieldList fields_hv();
@@ -298,6 +313,7 @@ void apply_cam_forcing(double dt, bool tracers);  // CamForcing.cpp:149-174 (tra
 void prim_diag_scalars(bool before_advance, int ivar);
 void prim_energy_halftimes(bool before_advance, int ivar);
 void push_Q_to_host(double* host_q);  // hxx_session.cu: device Q -> F90 layout
+void* diag_scratch(size_t bytes);     // hxx_session.cu: persistent device buffer of the diagnostic sums
 // remap.cu
 void vertical_remap(int np1, int np1_qdp, double dt);
 void check_remap_flag();

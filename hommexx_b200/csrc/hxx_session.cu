@@ -138,6 +138,15 @@ static void push_field(const double* dev, double* host, size_t nbatch, int C) {
   }
 }
 
+void* diag_scratch(size_t bytes) {
+  if (bytes > S.diag_scratch_bytes) {
+    if (S.diag_scratch) CUDA_OK(cudaFree(S.diag_scratch));
+    CUDA_OK(cudaMalloc(&S.diag_scratch, bytes));
+    S.diag_scratch_bytes = bytes;
+  }
+  return S.diag_scratch;
+}
+
 void push_Q_to_host(double* host_q) { push_field(S.Q, host_q, (size_t)S.nelemd * QSIZE_D, NPSQ); }
 
 static void free_all() {
@@ -152,6 +161,8 @@ static void free_all() {
   dfree(S.invalid_flag);
   if (S.h_invalid) { cudaFreeHost(S.h_invalid); S.h_invalid = nullptr; }
   if (S.scratch) { cudaFree(S.scratch); S.scratch = nullptr; S.scratch_bytes = 0; }
+  if (S.diag_scratch) { cudaFree(S.diag_scratch); S.diag_scratch = nullptr; S.diag_scratch_bytes = 0; }
+  for (auto& d : S.diag) d = nullptr;  // the F90 accumulators belong to the finished run
   S.conn.clear();
 }
 
@@ -342,6 +353,7 @@ void initialize_hommexx_session(void) {
   CUDA_OK(cudaEventCreateWithFlags(&S.ev_produced, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&S.ev_halo, cudaEventDisableTiming));
   S.active = true;
+  ++S.session_id;
   S.launches = 0;
   if (S.rank == 0 && std::getenv("HXX_BANNER"))
     std::printf("HOMMEXX-B200 session: %s, %d SMs, nlev=%d qsize_d=%d, ranks=%d\n", prop.name,
@@ -596,6 +608,7 @@ void prim_run_subcycle_c(const double* dt, int* nstep, int* nm1, int* n0, int* n
   // into its tracer store); without tracers there is nothing to update
   vertical_remap(S.np1, S.np1_qdp, dt_remap);
   check_remap_flag();                // RemapFunctor.hpp:190-198 (one host sync per call)
+  check_comm_errors();
   if (compute_diagnostics) {
     prim_diag_scalars(false, 1);
     prim_energy_halftimes(false, 1);

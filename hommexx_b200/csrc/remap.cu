@@ -439,6 +439,7 @@ void vertical_remap(int np1, int np1_qdp, double dt) {
   const RemapMap m = remap_map(S.p.qsize);
   const size_t smem = RC * sizeof(ColData) + (size_t)m.nwarps * STAGE_PER_WARP * sizeof(double);
   static size_t attr = 0;
+  if (HXX_ONCE_PER_SESSION()) attr = 0;
   if (smem > attr) {
     CUDA_OK(cudaFuncSetAttribute(remap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;

@@ -105,7 +105,8 @@ int hommexx_b200_qsize_d(void);  /* QSIZE_D of this build */
 const char* hommexx_b200_backend(void);
 /* One process per GPU. rank/size as in MPI_Comm_rank/size; device = CUDA device ordinal;
  * nccl_unique_id = the 128-byte ncclUniqueId created on rank 0 and broadcast by the host
- * (torch.distributed / MPI_Bcast). Must be called before init_connectivity when size > 1. */
+ * (torch.distributed / MPI_Bcast). Must be called BEFORE initialize_hommexx_session (the session
+ * binds the device and creates its streams there); a call on an active session aborts with code 13. */
 void hommexx_b200_set_comm(int rank, int size, int device, const void* nccl_unique_id);
 /* Fills out128 with a fresh ncclUniqueId (call on rank 0, broadcast, pass to set_comm).
  * Returns 0 on success, nonzero if NCCL is unavailable in this build. */

@@ -1,0 +1,157 @@
+"""Parity of the BENCHMARKED binary — libhommexx_b200_nlev72_q40.so, BASELINE configs[1] — against the CPU
+oracle, with 40 pairwise-distinct tracers (tests/distinct_tracers.py).
+
+The (72, 4) builds give every warp of the tracer kernels one tracer; only at qsize 40 do the multi-tracer
+cp.async pipelines of euler.cu wrap around their double buffers, does the remap's 43-field thread map
+(one full warp per column plus packed remainder lanes) exist, and does a DSS carry 41 fields in several
+grid.y chunks. The reference checks a whole step of its C++ build bit for bit against Fortran
+(cmake/CxxVsF90.cmake.in:28-41); the same is demanded here of CUDA against the oracle: north_star
+tolerance 1e-11 on the normalised L2 difference, and in fact tol = 0 (bit-identical) wherever stated."""
+import numpy as np
+import pytest
+
+import distinct_tracers
+import parity
+from hommexx_b200 import homme
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-11  # north_star
+
+
+def pair40(cfg):
+    """(cuda, oracle) on identical inputs with distinct tracers installed before the state is uploaded."""
+    parity.need_gpu()
+    hc = homme.Homme(cfg, parity.cuda_lib(cfg.nlev, cfg.qsize_d))
+    ho = homme.Homme(cfg, homme.ORACLE_LIB)
+    for h in (hc, ho):
+        q = distinct_tracers.install(h)
+        h.init_dycore()
+    distinct_tracers.assert_distinct(q)
+    assert hc.lib.hommexx_b200_backend() == b"cuda-sm100a" and ho.lib.hommexx_b200_backend() == b"cpu-oracle"
+    assert hc.lib.hommexx_b200_qsize_d() == cfg.qsize_d
+    return hc, ho
+
+
+def q40(name, **over):
+    over.setdefault("qsize", 40)
+    return homme.preset(name, qsize_d=40, **over)
+
+
+@pytest.fixture(scope="module")
+def warm40():
+    """ne4 / nlev 72 / qsize 40 after one subcycle call of the oracle: every field non-trivial."""
+    hc, ho = pair40(q40("ne4"))
+    ho.run_subcycle()
+    snap = {n: ho.get_field(n) for n in parity.STATE_FIELDS + ["qtens_biharmonic"]}
+    yield hc, ho, snap
+    hc.close(); ho.close()
+
+
+def _reset(warm):
+    hc, ho, snap = warm
+    for n, a in snap.items():
+        hc.set_field(n, a); ho.set_field(n, a)
+    return hc, ho
+
+
+def test_q40_euler_stages_parity(warm40):
+    """hxx_euler_step x 3 stages + qdp_time_avg at 40 tracers: 10 tracers per warp through the wrapped
+    cp.async double buffers of euler_qminmax / euler_hvpost / euler_advect."""
+    hc, ho = _reset(warm40)
+    for h in (hc, ho):
+        h.lib.hxx_euler_reset()
+        h.lib.hxx_euler_precompute_divdp()
+    for (np1q, n0q, rhs, opt) in [(1, 0, 0.0, 2), (1, 1, 1.0, 0), (1, 1, 2.0, 1)]:
+        for h in (hc, ho):
+            h.lib.hxx_euler_step(np1q, n0q, 900.0, rhs, opt)
+        parity.compare_fields(hc, ho, tol=0.0, what=f"q40 euler_step rhs_mult={rhs}")
+    for h in (hc, ho):
+        h.lib.hxx_euler_qdp_time_avg(0, 1)
+    parity.compare_fields(hc, ho, tol=0.0, what="q40 qdp_time_avg")
+    # the tracers are still pairwise distinct: nothing was copied across tracer slots
+    qdp = hc.get_field("qdp").reshape(hc.nelemd, 2, 40, 16, 72)
+    distinct_tracers.assert_distinct(qdp[:, 1].reshape(hc.nelemd, 40, 16, 72, 1))
+
+
+def test_q40_remap_parity(warm40):
+    """The production remap_kernel at nf = 43: one full warp of fields per column + the packed remainder."""
+    hc, ho = _reset(warm40)
+    qdp0 = ho.get_field("qdp").reshape(ho.nelemd, 2, 40, 16, 72).copy()
+    for h in (hc, ho):
+        h.lib.hxx_vertical_remap(2, 1, 5400.0)
+        h.lib.hxx_update_q(1, 2)
+    parity.compare_fields(hc, ho, tol=0.0, what="q40 vertical_remap/update_q")
+    qdp1 = hc.get_field("qdp").reshape(hc.nelemd, 2, 40, 16, 72)
+    assert np.allclose(qdp1[:, 1].sum(-1), qdp0[:, 1].sum(-1), rtol=1e-13, atol=0)   # column mass to round-off
+
+
+@pytest.mark.parametrize("fset,rsp", [("euler:1:0", 1), ("euler:0:1", 1), ("euler:0:2", 1), ("qtens", 1), ("qlim", 0)])
+def test_q40_exchange_parity(warm40, fset, rsp):
+    """DSS of 41 fields (6 grid.y chunks of 8) and the 40-tracer min/max exchange, random data."""
+    hc, ho = _reset(warm40)
+    rng = np.random.default_rng(40)
+    names = ["qdp", "qtens_biharmonic", "eta_dot_dpdn", "omega_p", "divdp_proj", "qlim"]
+    for name in names:
+        x = rng.standard_normal(ho.field_size(name))
+        hc.set_field(name, x); ho.set_field(name, x)
+    hc.lib.hxx_exchange(fset.encode(), rsp)
+    ho.lib.hxx_exchange(fset.encode(), rsp)
+    parity.compare_fields(hc, ho, names, tol=0.0, what=f"q40 {fset}")
+
+
+def test_q40_forcing_parity(warm40):
+    hc, ho = _reset(warm40)
+    for h in (hc, ho):
+        h.lib.hxx_apply_forcing(5400.0)
+    parity.compare_fields(hc, ho, tol=0.0, what="q40 apply_cam_forcing")
+
+
+CASES = {
+    # 12 dynamics steps at ne8 with the full tracer load of the headline configuration
+    "ne8-q40": dict(base="ne8"),
+    # option variants on the 40-tracer binary
+    "ne4-q40-lim9-alg2": dict(base="ne4", limiter_option=9, remap_alg=2),
+    "ne4-q40-r0": dict(base="ne4", rsplit=0),
+    # qsize < QSIZE_D: ragged tracer loops (35 = 8 full rounds of 4 warps + 3), remap nf = 38, moist CAAR reads tracer 0
+    "ne4-q35of40-moist-q2": dict(base="ne4", qsize=35, moisture=1, qsplit=2, rsplit=2),
+    "ne4-q1of40": dict(base="ne4", qsize=1),
+}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_q40_ten_step_parity(case):
+    over = dict(CASES[case])
+    cfg = q40(over.pop("base"), **over)
+    hc, ho = pair40(cfg)
+    nstep = 0
+    while nstep < 10:
+        nstep = hc.run_subcycle()
+        assert ho.run_subcycle() == nstep
+    assert hc.time_levels() == ho.time_levels()
+    hc.push_results(); ho.push_results()
+    sc, so = hc.state(), ho.state()
+    errs = {k: (0.0 if np.array_equal(sc[k], so[k]) else parity.rel_l2(sc[k], so[k])) for k in parity.PROGNOSTIC}
+    print(case, "steps", nstep, "rel-L2 vs oracle:", errs)
+    assert not any(np.isnan(so[k]).any() for k in so)
+    assert max(errs.values()) <= TOL, errs
+    hc.close(); ho.close()
+
+
+def test_ne30_q40_one_call_parity():
+    """BASELINE configs[1] itself: ne30 (5400 elements), nlev 72, qsize 40 — one prim_run_subcycle_c call
+    (3 dynamics steps, 9 tracer stages, one remap) of the benchmarked library against the oracle."""
+    cfg = q40("ne30")
+    hc, ho = pair40(cfg)
+    assert hc.nelem == 5400
+    sph = hc.array("spheremp").reshape(-1, 1, 1, 4, 4)
+    m0 = (hc.state()["Qdp"][:, 0] * sph).sum(axis=(0, 2, 3, 4))
+    assert hc.run_subcycle() == ho.run_subcycle() == 3
+    hc.push_results(); ho.push_results()
+    sc, so = hc.state(), ho.state()
+    errs = {k: (0.0 if np.array_equal(sc[k], so[k]) else parity.rel_l2(sc[k], so[k])) for k in parity.PROGNOSTIC}
+    print("ne30 q40 rel-L2 vs oracle:", errs)
+    assert max(errs.values()) <= TOL, errs
+    tq = (3 // cfg.qsplit) % 2
+    m1 = (sc["Qdp"][:, tq] * sph).sum(axis=(0, 2, 3, 4))
+    assert np.abs(m1 - m0).max() <= 1e-12 * np.abs(m0).max()    # every tracer's global mass to round-off
+    hc.close(); ho.close()
