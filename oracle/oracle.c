@@ -680,9 +680,18 @@ typedef struct {
  * :539-596 with the fixed order S,N,W,E per k then corners), optional rspheremp scaling. */
 static void exchange(const FieldRef* fields, int nf, bool rspheremp) {
   const int n = O.nelemd, nlev = O.nlev;
-  /* recv buffer: [ie][field][conn][4 pts][nlev]; zero = the "blackhole" for missing corners */
+  /* recv buffer: [ie][field][conn][4 pts][nlev], kept between calls as the reference's BuffersManager keeps
+     its buffers (mpi/BuffersManager.cpp:95-135); slots of MISSING connections are never read (the reference
+     points them at a zero-filled "blackhole" instead, BoundaryExchange.cpp:1003-1020: adding 0 is a no-op) */
   const size_t per_f = (size_t)8 * NP * nlev;
-  double* recv = (double*)calloc((size_t)n * nf * per_f, sizeof(double));
+  static double* recv = NULL;
+  static size_t recv_cap = 0;
+  if ((size_t)n * nf * per_f > recv_cap) {
+    free(recv);
+    recv_cap = (size_t)n * nf * per_f;
+    recv = (double*)malloc(recv_cap * sizeof(double));
+    if (!recv) runtime_abort("oracle: out of memory", 1);
+  }
 #pragma omp parallel for
   for (int ie = 0; ie < n; ++ie)
     for (int f = 0; f < nf; ++f)
@@ -707,6 +716,7 @@ static void exchange(const FieldRef* fields, int nf, bool rspheremp) {
       const double* rb = recv + ((size_t)ie * nf + f) * per_f;
       for (int k = 0; k < NP; ++k)
         for (int e = 0; e < 4; ++e) {
+          if (O.conn[ie * 8 + e].kind == 2) continue;
           double* fp = fld + (size_t)EDGE_PTS_FWD[e][k] * nlev;
           const double* rp = rb + ((size_t)e * NP + k) * nlev;
           for (int l = 0; l < nlev; ++l) fp[l] += rp[l];
@@ -723,7 +733,6 @@ static void exchange(const FieldRef* fields, int nf, bool rspheremp) {
           for (int l = 0; l < nlev; ++l) fld[IX(p, l)] *= r;
         }
     }
-  free(recv);
 }
 
 /* exchange_min_max on qlim (BoundaryExchange.cpp:620-849) */

@@ -41,7 +41,8 @@ def q40(name, **over):
 def warm40():
     """ne4 / nlev 72 / qsize 40 after one subcycle call of the oracle: every field non-trivial."""
     hc, ho = pair40(q40("ne4"))
-    ho.run_subcycle()
+    assert hc.run_subcycle() == ho.run_subcycle()     # both sessions hold the same time levels afterwards
+    assert hc.time_levels() == ho.time_levels()
     snap = {n: ho.get_field(n) for n in parity.STATE_FIELDS + ["qtens_biharmonic"]}
     yield hc, ho, snap
     hc.close(); ho.close()
