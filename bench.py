@@ -104,15 +104,18 @@ class ClockSampler:
 
 
 def workload(args, n_gpus):
-    """N=1: BASELINE configs[1] (ne30). N>1: weak scaling, ~5400 elements per GPU
-    (ne = round(sqrt(900 N)): 42, 60, 85 for N = 2, 4, 8), same namelist."""
+    """N=1: BASELINE configs[1] (ne30, homme-ne30-v1.nl). N>1: BASELINE configs[3], Jablonowski-Williamson at
+    ne120 (86 400 elements, homme-ne120-v1.nl) SFC-partitioned over the N GPUs: STRONG scaling over 2/4/8.
+    --weak restores the round-1 weak-scaling meshes (~5400 elements per GPU, ne = round(sqrt(900 N)))."""
     from hommexx_b200 import homme
     if args.ne:
         ne = args.ne
     elif n_gpus == 1:
         ne = 30
-    else:
+    elif args.weak:
         ne = int(round((900.0 * n_gpus) ** 0.5))
+    else:
+        ne = 120
     over = dict(ne=ne, npart=n_gpus)
     if ne == 120:  # BASELINE configs[3]: the reference's own ne120 namelist (homme-ne120-v1.nl)
         if args.qsize:
@@ -173,17 +176,18 @@ def run_reference(args):
         h.run_subcycle()
     dt = time.perf_counter() - t0
     val = h.nelem * dyn * args.steps / dt
-    sample = (f"oracle port (CPU restatement of the reference functors, gcc -O3 -fopenmp), ne={ne_s} "
-              f"({h.nelem} elements) nlev {scfg.nlev} qsize {scfg.qsize}, same namelist as the GPU arm; "
-              f"element-steps/s is per-element throughput, so the sample is size-independent")
+    sample = (f"oracle port (CPU restatement of the reference functors, {flags}), OpenMP over elements on "
+              f"{cores} host threads, ne={ne_s} ({h.nelem} elements) nlev {scfg.nlev} qsize {scfg.qsize}, "
+              f"homme-ne30-v1.nl namelist, {args.steps} prim_run_subcycle_c calls after {args.warmup} warm-up")
     h.close()
     out = {"impl": "reference", "metric": "element_steps_per_s", "value": val, "unit": "element-steps/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "sypd": None,
-           "config": {"workload": f"preqx ne{cfg.ne} nlev{cfg.nlev} qsize{cfg.qsize} (timed on a bounded sample)",
-                      "sample": sample},
-           "cpu_baseline": {"value": val, "unit": "element-steps/s", "cores": cores, "kind": "port", "sample": sample},
+           "config": {"workload": f"preqx ne{cfg.ne} nlev{cfg.nlev} qsize{cfg.qsize}", "sample": sample,
+                      "same_config": ne_s == cfg.ne},
+           "cpu_baseline": {"value": val, "unit": "element-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                            "same_config": ne_s == cfg.ne},
            "e2e": {"value": val, "unit": "element-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)
@@ -209,7 +213,9 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--ne", type=int, default=0, help="override the mesh (default: 30 at N=1, weak-scaled for N>1)")
     ap.add_argument("--qsize", type=int, default=0)
-    ap.add_argument("--ref-ne", type=int, default=10, help="mesh of the bounded CPU sample")
+    ap.add_argument("--ref-ne", type=int, default=0, help="mesh of the bounded CPU sample (default: ne30 itself)")
+    ap.add_argument("--weak", action="store_true", help="N>1: weak-scaling meshes instead of ne120 strong scaling")
+    ap.add_argument("--no-fma", action="store_true", help="skip the timing of the FMA-contracted build")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -297,6 +303,7 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    nelem_global, nelem_local = h.nelem, h.nelemd
     value = h.nelem * dyn * args.steps / (ms * 1e-3)
     sypd = (dyn * args.steps / (ms * 1e-3)) * cfg.tstep / 365.0  # simulated years per wall day
 
@@ -370,41 +377,96 @@ def main():
                "what": "init_elements_states_c + steps x prim_run_subcycle_c + cxx_push_results_to_f90 from pinned "
                        "host arrays in the Fortran layout (the reference benchmark pushes once per run: statefreq=9999)"}
 
+    # ---- the CAM-coupled pattern: forcing pushed and results pulled on EVERY call ----------------
+    e2e_coupled = None
+    if not args.no_e2e and n_gpus == 1:
+        for name in ("FM", "FT", "FQ"):
+            a = h.array(name)
+            torch.cuda.cudart().cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+        fo = h.forcing()
+        nrep = max(2, min(5, args.steps))
+        h2d_c = sum(fo[k].nbytes for k in ("FM", "FT", "FQ"))
+        d2h_c = d2h + st["Qdp"].nbytes
+        h.push_forcing()            # first use allocates the device forcing arrays
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            h.push_forcing()        # f90_push_forcing_to_cxx: FM, FT, FQ host -> device, Qdp device -> host
+            h.run_subcycle()
+            h.push_results()        # cxx_push_results_to_f90
+        barrier()
+        c_s = time.perf_counter() - t0
+        e2e_coupled = {"value": h.nelem * dyn * nrep / c_s, "unit": "element-steps/s", "calls": nrep,
+                       "h2d_bytes_per_step": h2d_c, "d2h_bytes_per_step": d2h_c,
+                       "what": "per call: f90_push_forcing_to_cxx + prim_run_subcycle_c + cxx_push_results_to_f90 "
+                               "(prim_driver_mod.F90:1322-1404, the pattern of a CAM-coupled run); PCIe-bound"}
+
+    # ---- the FMA-contracted build of the same sources (parity <= 1e-11, tests/test_cuda_q40.py) ----
+    fma = None
+    fma_path = homme.cuda_lib_path(cfg.nlev, cfg.qsize_d, "fma")
+    if not args.no_fma and n_gpus == 1 and fma_path.exists():
+        h.close()
+        h = None
+        hf = homme.Homme(cfg, fma_path)
+        lf = hf.lib
+        lf.hommexx_b200_event_elapsed_ms.restype = C.c_double
+        lf.hommexx_b200_set_comm(0, 1, local_rank, None)
+        hf.init_dycore()
+        for _ in range(args.warmup):
+            hf.run_subcycle()
+        lf.hommexx_b200_sync()
+        lf.hommexx_b200_event_record(0)
+        for _ in range(args.steps):
+            hf.run_subcycle()
+        lf.hommexx_b200_event_record(1)
+        lf.hommexx_b200_sync()
+        fms = lf.hommexx_b200_event_elapsed_ms(0, 1)
+        fma = {"value": hf.nelem * dyn * args.steps / (fms * 1e-3), "unit": "element-steps/s",
+               "ms_per_step": fms / args.steps, "library": fma_path.name,
+               "what": "same sources compiled with --fmad=true (multiply-adds contracted); matches the oracle to "
+                       "<= 1e-11 on v, T, dp3d, ps, Qdp, Q after 10 steps instead of bit for bit"}
+        hf.close()
+
     # ---- CPU baseline beside it (rank 0, N = 1) -------------------------------------------------
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        scfg = homme.preset("ne30", ne=args.ref_ne, qsize=cfg.qsize)
-        ho = homme.Homme(scfg, homme.ORACLE_LIB)
+        os.environ["OMP_NUM_THREADS"] = str(cores)
+        olib, flags = native_oracle()
+        ne_s = cpu_sample_mesh(args, cores)
+        scfg = homme.preset("ne30", ne=ne_s, qsize=cfg.qsize)
+        ho = homme.Homme(scfg, olib)
         ho.init_dycore()
         ho.run_subcycle()
         t0 = time.perf_counter()
-        nrep = 8
+        nrep = 2
         for _ in range(nrep):
             ho.run_subcycle()
         dt = time.perf_counter() - t0
         cpu = {"value": ho.nelem * dyn * nrep / dt, "unit": "element-steps/s", "cores": cores, "kind": "port",
-               "sample": f"oracle port, {nrep} subcycle calls at ne={args.ref_ne} ({ho.nelem} elements), nlev {scfg.nlev}, "
-                         f"qsize {scfg.qsize}, OpenMP over elements on all host cores"}
+               "same_config": ne_s == cfg.ne,
+               "sample": f"oracle port ({flags}), {nrep} prim_run_subcycle_c calls at ne={ne_s} ({ho.nelem} elements), "
+                         f"nlev {scfg.nlev}, qsize {scfg.qsize}, OpenMP over elements on {cores} host threads"}
         ho.close()
 
     if rank == 0:
         out = {"metric": "element_steps_per_s", "value": value, "unit": "element-steps/s", "n_gpus": n_gpus,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-               "scaling": "strong" if (args.ne and n_gpus > 1) else "weak", "vs_baseline": None, "dtype": "f64",
+               "scaling": "weak" if (args.weak or n_gpus == 1) else "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "sypd": sypd, "dynamics_steps_per_bench_step": dyn,
-               "config": {"workload": f"preqx ne{cfg.ne} ({h.nelem} elements) nlev{cfg.nlev} qsize{cfg.qsize}, JW baroclinic "
+               "config": {"workload": f"preqx ne{cfg.ne} ({nelem_global} elements) nlev{cfg.nlev} qsize{cfg.qsize}, JW baroclinic "
                                       f"wave, homme-ne{120 if cfg.ne == 120 else 30}-v1.nl namelist (tstep {cfg.tstep:g} rsplit {cfg.rsplit} qsplit "
                                       f"{cfg.qsplit} hypervis_subcycle {cfg.hypervis_subcycle} limiter {cfg.limiter_option})",
-                          "partition": f"SFC, {n_gpus} part(s), {h.nelemd} elements on rank 0",
+                          "partition": f"SFC, {n_gpus} part(s), {nelem_local} elements on rank 0",
                           "l2": "working set (>9 GB at ne30) far exceeds the 126 MB L2; no flush needed",
                           "step": "one prim_run_subcycle_c call"},
                "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
                "step_roofline": {"algorithmic_bytes_per_element_step": step_bytes, "achieved_gbs_per_gpu": step_gbs,
                                  "frac": step_gbs / peak, "peak": peak},
-               "e2e": e2e, "cpu_baseline": cpu, "breakdown": breakdown}
+               "e2e": e2e, "e2e_coupled": e2e_coupled, "fma_build": fma, "cpu_baseline": cpu, "breakdown": breakdown}
         emit(out)
-    h.close()
+    if h is not None:
+        h.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

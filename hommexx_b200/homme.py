@@ -20,12 +20,13 @@ DRIVER_LIB = PKG / "driver" / "libhomme_driver.so"
 ORACLE_LIB = ROOT / "oracle" / "liboracle.so"
 
 
-def cuda_lib_path(nlev: int, qsize_d: int) -> pathlib.Path:
-    # HXX_VARIANT selects an experimental build of the same sources (scripts/build_variant.py);
-    # unset = the product library
+def cuda_lib_path(nlev: int, qsize_d: int, flavour: str = "") -> pathlib.Path:
+    """flavour "" = the strict build (--fmad=false, bit-identical to the oracle); "fma" = the same sources with
+    multiply-adds contracted (parity <= 1e-11). HXX_VARIANT selects an experimental build of the same sources
+    (scripts/build_variant.py) instead."""
     var = os.environ.get("HXX_VARIANT", "")
     base = PKG / "csrc" / "variants" / var if var else PKG / "csrc"
-    return base / f"libhommexx_b200_nlev{nlev}_q{qsize_d}.so"
+    return base / f"libhommexx_b200_nlev{nlev}_q{qsize_d}{'_' + flavour if flavour else ''}.so"
 
 
 class HommeParams(C.Structure):
