@@ -30,7 +30,7 @@ namespace hxx {
 static const int EDGE_PTS[4][4] = {{0, 1, 2, 3}, {12, 13, 14, 15}, {0, 4, 8, 12}, {3, 7, 11, 15}};
 static const int CORNER_PTS[4] = {0, 3, 12, 15};
 
-constexpr int NODES_PB = (NLEV * 4 <= 288) ? 4 : 2;  // nodes per block
+
 constexpr int DSS_FPB = 8;                           // fields per thread (grid.y chunks)
 
 #ifndef HXX_DSS_PAIR_UB
@@ -48,18 +48,17 @@ constexpr int DSS_FPB = 8;                           // fields per thread (grid.
 constexpr int DSS_FB = HXX_DSS_FB;  // fields whose loads are in flight together in one thread
 
 template <bool RSP, bool AVG>
-__global__ void __launch_bounds__(NODES_PB* NLEV, HXX_DSS_MINB)
-    dss_nodes_kernel(const DssNode* __restrict__ nodes, int nnodes, FieldList fl, const double* __restrict__ geo,
-                     const double* __restrict__ halo) {
-  const int nl = threadIdx.x / NLEV, k = threadIdx.x % NLEV;
-  const int node = blockIdx.x * NODES_PB + nl;
+__device__ __forceinline__ void dss_nodes_body(const DssNode* __restrict__ nodes, int nnodes, const FieldList& fl,
+                                               const double* __restrict__ geo, const double* __restrict__ halo,
+                                               long long g, int ychunk) {
+  const int node = (int)(g / NLEV), k = (int)(g % NLEV);
   if (node >= nnodes) return;
   const DssNode nd = nodes[node];
   double rs[4];
 #pragma unroll
   for (int m = 0; m < 4; ++m)
     rs[m] = (RSP && m < nd.nmem && nd.src[m] >= 0) ? __ldg(geo + (size_t)nd.src[m] * GEO_N + G_RSPHEREMP) : 1.0;
-  const int f0 = blockIdx.y * DSS_FPB, f1 = min(fl.nf, f0 + DSS_FPB);
+  const int f0 = ychunk * DSS_FPB, f1 = min(fl.nf, f0 + DSS_FPB);
   for (int fb = f0; fb < f1; fb += DSS_FB) {
     // the loads of DSS_FB fields are issued before the first store (the fields may alias as far
     // as the compiler knows, which would otherwise serialise load -> store -> load)
@@ -127,9 +126,8 @@ static_assert(sizeof(DssQuad) == 32, "DssQuad layout");
 constexpr int DSS_TPB = 128;
 
 template <bool RSP, bool AVG>
-__global__ void __launch_bounds__(DSS_TPB)
-    dss_pair_kernel(const DssPair* __restrict__ pairs, int npairs, FieldList fl, const double* __restrict__ geo) {
-  const long long g = (long long)blockIdx.x * DSS_TPB + threadIdx.x;
+__device__ __forceinline__ void dss_pair_body(const DssPair* __restrict__ pairs, int npairs, const FieldList& fl,
+                                              const double* __restrict__ geo, long long g, int ychunk) {
   const int ip = (int)(g / NLEV), k = (int)(g % NLEV);
   if (ip >= npairs) return;
   const DssPair pr = pairs[ip];
@@ -140,7 +138,7 @@ __global__ void __launch_bounds__(DSS_TPB)
     ra = __ldg(geo + (size_t)pr.a * GEO_N + G_RSPHEREMP);
     rb = __ldg(geo + (size_t)pr.b * GEO_N + G_RSPHEREMP);
   }
-  const int f0 = blockIdx.y * DSS_FPB, f1 = min(fl.nf, f0 + DSS_FPB);
+  const int f0 = ychunk * DSS_FPB, f1 = min(fl.nf, f0 + DSS_FPB);
   constexpr int UB = HXX_DSS_PAIR_UB;  // fields whose loads are issued before the first store
   for (int fb = f0; fb < f1; fb += UB) {
     double *pa[UB], *pb[UB];
@@ -177,9 +175,8 @@ __global__ void __launch_bounds__(DSS_TPB)
 }
 
 template <bool RSP, bool AVG>
-__global__ void __launch_bounds__(DSS_TPB)
-    dss_quad_kernel(const DssQuad* __restrict__ quads, int nquads, FieldList fl, const double* __restrict__ geo) {
-  const long long g = (long long)blockIdx.x * DSS_TPB + threadIdx.x;
+__device__ __forceinline__ void dss_quad_body(const DssQuad* __restrict__ quads, int nquads, const FieldList& fl,
+                                              const double* __restrict__ geo, long long g, int ychunk) {
   const int iq = (int)(g / NLEV), k = (int)(g % NLEV);
   if (iq >= nquads) return;
   const DssQuad qd = quads[iq];
@@ -193,7 +190,7 @@ __global__ void __launch_bounds__(DSS_TPB)
     rs[m] = RSP ? __ldg(geo + (size_t)qd.m[m] * GEO_N + G_RSPHEREMP) : 1.0;
   }
   const bool s1 = qd.swaps & 1, s2 = qd.swaps & 2, s3 = qd.swaps & 4;
-  const int f0 = blockIdx.y * DSS_FPB, f1 = min(fl.nf, f0 + DSS_FPB);
+  const int f0 = ychunk * DSS_FPB, f1 = min(fl.nf, f0 + DSS_FPB);
   constexpr int UB = HXX_DSS_QUAD_UB;
   for (int fb = f0; fb < f1; fb += UB) {
     double* ptr[UB][4];
@@ -229,6 +226,31 @@ __global__ void __launch_bounds__(DSS_TPB)
       }
     }
   }
+}
+
+// One launch per exchange: blocks [0, nb_pair) take the pair list, the next nb_quad blocks the quad list and
+// the rest the generic nodes (the split is block-uniform, so nothing diverges). On several ranks the generic
+// nodes read the halo and are launched on their own once it has landed (nb_node = 0 here).
+struct DssLists {
+  const DssPair* pairs; int npairs, nb_pair;
+  const DssQuad* quads; int nquads, nb_quad;
+  const DssNode* nodes; int nnodes;
+  const double* halo;
+};
+template <bool RSP, bool AVG>
+__global__ void __launch_bounds__(DSS_TPB, HXX_DSS_MINB) dss_kernel(DssLists L, FieldList fl, const double* __restrict__ geo) {
+  int b = blockIdx.x;
+  if (b < L.nb_pair) {
+    dss_pair_body<RSP, AVG>(L.pairs, L.npairs, fl, geo, (long long)b * DSS_TPB + threadIdx.x, blockIdx.y);
+    return;
+  }
+  b -= L.nb_pair;
+  if (b < L.nb_quad) {
+    dss_quad_body<RSP, AVG>(L.quads, L.nquads, fl, geo, (long long)b * DSS_TPB + threadIdx.x, blockIdx.y);
+    return;
+  }
+  b -= L.nb_quad;
+  dss_nodes_body<RSP, AVG>(L.nodes, L.nnodes, fl, geo, L.halo, (long long)b * DSS_TPB + threadIdx.x, blockIdx.y);
 }
 
 __global__ void scale_interior_kernel(FieldList fl, const double* __restrict__ geo, int nelem) {
@@ -582,40 +604,25 @@ void dss_exchange(const FieldList& fl, bool rspheremp) {
   }
   const int ny = (fl.nf + DSS_FPB - 1) / DSS_FPB;
   const bool avg = fl.navg > 0;
-#define HXX_DSS_LAUNCH(KERNEL, GRID, BLOCK, ...)                                             \
-  do {                                                                                       \
-    PROBE(K_DSS);                                                                            \
-    if (avg && rspheremp) KERNEL<true, true><<<GRID, BLOCK, 0, S.stream>>>(__VA_ARGS__);     \
-    else if (avg) KERNEL<false, true><<<GRID, BLOCK, 0, S.stream>>>(__VA_ARGS__);            \
-    else if (rspheremp) KERNEL<true, false><<<GRID, BLOCK, 0, S.stream>>>(__VA_ARGS__);      \
-    else KERNEL<false, false><<<GRID, BLOCK, 0, S.stream>>>(__VA_ARGS__);                    \
-    KERNEL_LAUNCHED(K_DSS);                                                                  \
-  } while (0)
-  if (S.npairs) {
-    const dim3 grid((unsigned)(((long long)S.npairs * NLEV + DSS_TPB - 1) / DSS_TPB), ny);
-    HXX_DSS_LAUNCH(dss_pair_kernel, grid, DSS_TPB, (const DssPair*)S.dss_pairs, S.npairs, fl, S.geo);
+  auto nblk = [](int n) { return (int)(((long long)n * NLEV + DSS_TPB - 1) / DSS_TPB); };
+  auto launch = [&](const DssLists& L, int nb) {
+    if (!nb) return;
+    const dim3 grid(nb, ny);
+    PROBE(K_DSS);
+    if (avg && rspheremp) dss_kernel<true, true><<<grid, DSS_TPB, 0, S.stream>>>(L, fl, S.geo);
+    else if (avg) dss_kernel<false, true><<<grid, DSS_TPB, 0, S.stream>>>(L, fl, S.geo);
+    else if (rspheremp) dss_kernel<true, false><<<grid, DSS_TPB, 0, S.stream>>>(L, fl, S.geo);
+    else dss_kernel<false, false><<<grid, DSS_TPB, 0, S.stream>>>(L, fl, S.geo);
+    KERNEL_LAUNCHED(K_DSS);
+  };
+  DssLists L{(const DssPair*)S.dss_pairs, S.npairs, nblk(S.npairs), (const DssQuad*)S.dss_quads, S.nquads, nblk(S.nquads),
+             S.nodes, halo ? 0 : S.nnodes, S.recvbuf};
+  launch(L, L.nb_pair + L.nb_quad + nblk(L.nnodes));
+  if (halo) {
+    CUDA_OK(cudaStreamWaitEvent(S.stream, S.ev_halo, 0));
+    DssLists G{nullptr, 0, 0, nullptr, 0, 0, S.nodes, S.nnodes, S.recvbuf};
+    launch(G, nblk(S.nnodes));
   }
-  if (S.nquads) {
-    const dim3 grid((unsigned)(((long long)S.nquads * NLEV + DSS_TPB - 1) / DSS_TPB), ny);
-    HXX_DSS_LAUNCH(dss_quad_kernel, grid, DSS_TPB, (const DssQuad*)S.dss_quads, S.nquads, fl, S.geo);
-  }
-  if (halo) CUDA_OK(cudaStreamWaitEvent(S.stream, S.ev_halo, 0));
-  if (S.nnodes) {
-    const dim3 grid((S.nnodes + NODES_PB - 1) / NODES_PB, ny);
-    HXX_DSS_LAUNCH(dss_nodes_kernel, grid, NODES_PB * NLEV, S.nodes, S.nnodes, fl, S.geo, S.recvbuf);
-  }
-#undef HXX_DSS_LAUNCH
-}
-
-// Asynchronous NCCL errors (a peer that died) surface here instead of as a hang; polled once per
-// prim_run_subcycle_c, next to the remap's abort flag.
-void check_comm_errors() {
-#ifdef HXX_WITH_NCCL
-  if (!S.nccl) return;
-  ncclResult_t st = ncclSuccess;
-  if (ncclCommGetAsyncError((ncclComm_t)S.nccl, &st) != ncclSuccess || (st != ncclSuccess && st != ncclInProgress))
-    runtime_abort("halo exchange: asynchronous NCCL error (a peer rank failed?)", 1);
-#endif
 }
 
 void scale_interior_rspheremp(const FieldList& fl) {

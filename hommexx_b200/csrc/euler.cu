@@ -176,9 +176,12 @@ static_assert(NPSQ % ADV_NW == 0, "the warps split the 16 points of the set-up e
 // time-average partners and, on the hyperviscosity stage, the prepared term (16)
 template <bool HV>
 __host__ __device__ constexpr int advect_stage_slots() { return NPSQ + 2 + 4 + (HV ? NPSQ : 0); }
-// doubles of dynamic shared memory: 5 constant planes + the weight sum, then the warps' staging slots
-template <bool HV>
-__host__ __device__ constexpr int advect_smem_doubles() { return (5 * NPSQ + 1) * 32 + ADV_NW * advect_stage_slots<HV>() * 32; }
+// doubles of dynamic shared memory: 5 constant planes + the weight sum (+ dp and 1/dp when the kernel also
+// does the stage's min/max pass, MM), then the warps' staging slots
+template <bool HV, bool MM = false>
+__host__ __device__ constexpr int advect_smem_doubles() {
+  return (5 * NPSQ + 1 + (MM ? 2 * NPSQ : 0)) * 32 + ADV_NW * advect_stage_slots<HV>() * 32;
+}
 
 // compute_biharmonic_post :216-231 with rhsviss_adjustment :293-310, in place:
 // qtens_biharmonic <- (-rhs_viss dt nu_q) dp0 laplace(qtens_biharmonic) / spheremp
@@ -227,7 +230,10 @@ __global__ void __launch_bounds__(TPB, HXX_HVPOST_MINB) euler_hvpost_kernel(cons
 
 // advect_and_limit :317-332 = compute_2d_advection_step (:585-626) + run_tracer_phase (:571-582).
 // HV: the hyperviscosity term prepared in place by euler_hvpost_kernel is added (:216-231).
-template <bool HV, bool TAVG>
+// MM: the stage with rhs_multiplier == 1 has no neighbour exchange between its min/max pass (compute_qmin_qmax
+// :436-485, qmin = min(qmin, Q), Q = Qdp / dp) and the limiter, and both read the same Qdp plane: the kernel
+// forms Q from the plane it has just staged and widens the limits itself, so the tracers are read once.
+template <bool HV, bool TAVG, bool MM = false>
 __global__ void __launch_bounds__(ADV_T, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) euler_advect_kernel(const EulerArgs a) {
   extern __shared__ double s_all[];
   __shared__ double s_geo[geo_span(32) * NPSQ * GEO_N];
@@ -244,7 +250,9 @@ __global__ void __launch_bounds__(ADV_T, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eu
   double* const s_rdpk = s_all + 48 * 32 + lane;
   double* const s_c = s_all + 64 * 32 + lane;
   double* const s_sumc = s_all + 80 * 32 + lane;
-  double* const s_q = s_all + 81 * 32 + w * advect_stage_slots<HV>() * 32 + lane;  // this warp's staging slots
+  double* const s_dp = s_all + 81 * 32 + lane;             // MM only: dp of compute_dp (:406-434) and 1 / dp
+  double* const s_rdp = s_all + (81 + NPSQ) * 32 + lane;
+  double* const s_q = s_all + (81 + (MM ? 2 * NPSQ : 0)) * 32 + w * advect_stage_slots<HV>() * 32 + lane;  // this warp's staging slots
   double* const s_l = s_q + NPSQ * 32;  // qlim rows
   double* const s_a = s_l + 2 * 32;     // time-average partners (qdp_time_avg :379-403, interior points)
   double* const s_b = s_a + 4 * 32;     // HV: the prepared term
@@ -307,6 +315,7 @@ __global__ void __launch_bounds__(ADV_T, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eu
       const double rdp = 1.0 / dp;
       s_vs0[p * 32] = div_rcp(r3[i], dp, rdp);
       s_vs1[p * 32] = div_rcp(r4[i], dp, rdp);
+      if (MM) { s_dp[p * 32] = dp; s_rdp[p * 32] = rdp; }
       double d = dp - a.dt * r2[i];
       if (add_ps_diss) d += div_rcp(diss_fac * r5[i], sm_, geo_ld(g, p, G_INV_SPHEREMP));
       s_dpk[p * 32] = d;
@@ -342,6 +351,29 @@ __global__ void __launch_bounds__(ADV_T, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eu
     double x[NPSQ];
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) x[p] = s_q[p * 32];
+    double qmin = qmin0, qmax = qmax0;
+    if (MM) {  // compute_qmin_qmax :436-485 on the plane just staged; same quotient as euler_qminmax_kernel
+      unsigned worst = 0;
+      HXX_UNROLL
+      for (int p = 0; p < NPSQ; ++p) worst = max(worst, (((unsigned)__double2hiint(x[p]) >> 20) & 0x7ffu) - 423u);
+      if (worst <= 1200u) {
+        HXX_UNROLL
+        for (int p = 0; p < NPSQ; ++p) {
+          const double dd = s_dp[p * 32], rr = s_rdp[p * 32];
+          const double q = x[p] * rr;
+          const double Q = fma(fma(-dd, q, x[p]), rr, q);
+          qmin = fmin(qmin, Q);
+          qmax = fmax(qmax, Q);
+        }
+      } else {
+        HXX_UNROLL
+        for (int p = 0; p < NPSQ; ++p) {
+          const double Q = div_rcp(x[p], s_dp[p * 32], s_rdp[p * 32]);
+          qmin = fmin(qmin, Q);
+          qmax = fmax(qmax, Q);
+        }
+      }
+    }
     {
       // divergence_sphere_update, SphereOperators.hpp:398-444
       double gv0[NPSQ], gv1[NPSQ];
@@ -384,15 +416,14 @@ __global__ void __launch_bounds__(ADV_T, HV ? HXX_ADV_MINB_HV : HXX_ADV_MINB) eu
     prefetch(q + ADV_NW);
     // limiter shell :693-761; a level whose weights do not sum to a positive number is left alone
     if (!skip) {
-      double qmin = qmin0, qmax = qmax0;
       div_rcp_plane(x, [&](int p) { return s_dpk[p * 32]; }, [&](int p) { return s_rdpk[p * 32]; });
       limiter_level_w(a.limiter_option, SlotPlane{s_c, 32}, sumc, x, qmin, qmax);
       HXX_UNROLL
       for (int p = 0; p < NPSQ; ++p) x[p] = x[p] * s_dpk[p * 32];
-      if (valid) {
-        if (qmin != qmin0) qlp[0] = qmin;
-        if (qmax != qmax0) qlp[NLEV] = qmax;
-      }
+    }
+    if (valid) {  // only the limits that moved (qmin0, qmax0 are what memory holds); MM: always, two registers less
+      if (MM || qmin != qmin0) qlp[0] = qmin;
+      if (MM || qmax != qmax0) qlp[NLEV] = qmax;
     }
     HXX_UNROLL
     for (int p = 0; p < NPSQ; ++p) {  // apply_spheremp :672-687
@@ -456,6 +487,9 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
               n0_qdp, np1_qdp, dt, rhs_multiplier * dt, S.p.nu_p, S.p.nu_q, S.rhs_viss, mode, tavg_n0_qdp, S.p.limiter_option,
               S.p.consthv ? 1 : 0};
   const dim3 grid(nblocks_flat(S.nelemd), (nq + a.qchunk - 1) / a.qchunk);
+  // rhs_multiplier == 1 (no exchange between the min/max pass and the limiter): the advection kernel does both
+  const bool fuse_mm = mode == 1 && S.rhs_viss == 0.0 && tavg_n0_qdp < 0;
+  if (!fuse_mm) {
   PROBE(K_EULER_QMINMAX);
   {
     if (HXX_ONCE_PER_SESSION()) {
@@ -469,6 +503,7 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
     else euler_qminmax_kernel<false><<<nb32, BIH_T, bih_smem_doubles * sizeof(double), S.stream>>>(a);
   }
   KERNEL_LAUNCHED(K_EULER_QMINMAX);
+  }
   if (mode == 0) {
     minmax_exchange();  // neighbor_minmax :504-507
   } else if (mode == 2) {
@@ -480,7 +515,8 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   a.qlim = S.qlim;  // minmax_exchange swaps the double buffer
   const bool hv = S.rhs_viss != 0.0;
   const bool tavg = tavg_n0_qdp >= 0;
-  const size_t smem = (size_t)(hv ? advect_smem_doubles<true>() : advect_smem_doubles<false>()) * sizeof(double);
+  const size_t smem = (size_t)(hv ? advect_smem_doubles<true>() : fuse_mm ? advect_smem_doubles<false, true>()
+                                                                           : advect_smem_doubles<false>()) * sizeof(double);
   const int adv_blocks = (int)(((long long)S.nelemd * NLEV + 31) / 32);
   if (HXX_ONCE_PER_SESSION()) {
 #define HXX_ADV_ATTR(H, T)                                                                                  \
@@ -488,6 +524,8 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
                                advect_smem_doubles<H>() * (int)sizeof(double)))
     HXX_ADV_ATTR(false, false); HXX_ADV_ATTR(false, true); HXX_ADV_ATTR(true, false); HXX_ADV_ATTR(true, true);
 #undef HXX_ADV_ATTR
+    CUDA_OK(cudaFuncSetAttribute(euler_advect_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 advect_smem_doubles<false, true>() * (int)sizeof(double)));
   }
   if (hv && !HV_FUSED) {  // compute_biharmonic_post: the second Laplacian, in place
     if (HXX_ONCE_PER_SESSION()) {
@@ -507,6 +545,7 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   if (hv && tavg) euler_advect_kernel<true, true><<<adv_blocks, ADV_T, smem, S.stream>>>(a);
   else if (hv) euler_advect_kernel<true, false><<<adv_blocks, ADV_T, smem, S.stream>>>(a);
   else if (tavg) euler_advect_kernel<false, true><<<adv_blocks, ADV_T, smem, S.stream>>>(a);
+  else if (fuse_mm) euler_advect_kernel<false, false, true><<<adv_blocks, ADV_T, smem, S.stream>>>(a);
   else euler_advect_kernel<false, false><<<adv_blocks, ADV_T, smem, S.stream>>>(a);
   KERNEL_LAUNCHED(K_EULER_ADVECT);
   if (separate) {
