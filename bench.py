@@ -197,7 +197,10 @@ def pin_driver_arrays(h, torch):
     """Page-lock the driver's Fortran-layout arrays so the e2e copies run from pinned memory."""
     rt = torch.cuda.cudart()
     pinned = []
-    for name in ("v", "T", "dp3d", "Qdp", "Q", "ps_v", "omega_p"):
+    names = ("v", "T", "dp3d", "Qdp", "Q", "ps_v", "omega_p")
+    if sum(h.array(n).nbytes for n in names) > (32 << 30):
+        return pinned   # ne120 shards: tens of GB per rank; page-locking that much is slow and can fail
+    for name in names:
         a = h.array(name)
         r = rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
         if int(r) == 0:

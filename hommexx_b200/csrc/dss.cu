@@ -15,6 +15,7 @@
 // order agreed by sorting connections on (owner gid, owner pos), cf. BoundaryExchange.cpp:1050).
 #include <algorithm>
 #include <array>
+#include <cstring>
 #include <map>
 #include <tuple>
 #include <unordered_map>
@@ -273,6 +274,58 @@ __global__ void halo_pack_kernel(const int* __restrict__ send_src, int npts, Fie
   for (int k = threadIdx.x; k < NLEV; k += blockDim.x) dst[k] = src[k];
 }
 
+// ---- P2P halo over NVLink -----------------------------------------------------------------------
+// Every rank maps its neighbours' receive buffers (CUDA IPC) and the pack kernels store the boundary
+// points straight into them: no send buffer, no NCCL launch. An exchange is numbered (epoch, the same
+// sequence on every rank) and uses receive buffer epoch & 1; after the pack a one-warp kernel publishes
+// the epoch in the neighbours' flag words (fence + release at system scope), and the consumer stream
+// runs a one-warp kernel that spins on this rank's own flags (acquire at system scope) before the kernel
+// that reads the halo. Two buffers suffice: a rank can pack exchange n only after it consumed exchange
+// n - 1 from each neighbour, and the neighbour packed n - 1 after it had consumed n - 2.
+constexpr int MAX_PEERS = 16;
+struct HaloPeers {
+  double* recv[2][MAX_PEERS];  // the peers' receive buffers (mapped)
+  int* flags[MAX_PEERS];       // the peers' flag arrays (mapped), indexed by sender rank
+  int rank_of[MAX_PEERS];
+  int npeers, my_rank;
+};
+static HaloPeers g_peers;
+
+__global__ void halo_pack_p2p_kernel(const int* __restrict__ send_src, const int* __restrict__ dst_pt,
+                                     const int* __restrict__ dst_peer, FieldList fl, HaloPeers P, int sel) {
+  const int i = blockIdx.x, f = blockIdx.y;
+  const int s = send_src[i];
+  const double* src = fl.base[f] + (size_t)(s >> 4) * fl.estride[f] + (s & 15) * NLEV;
+  double* dst = P.recv[sel][dst_peer[i]] + ((size_t)dst_pt[i] * fl.nf + f) * NLEV;
+  for (int k = threadIdx.x; k < NLEV; k += blockDim.x) dst[k] = src[k];
+}
+__global__ void minmax_pack_p2p_kernel(const int* __restrict__ send_elem, const int* __restrict__ dst_conn,
+                                       const int* __restrict__ dst_peer, const double* __restrict__ qlim, int qsize,
+                                       HaloPeers P, int sel) {
+  const int i = blockIdx.x, q = blockIdx.y;
+  const double* src = qlim + ((size_t)send_elem[i] * QSIZE_D + q) * 2 * NLEV;
+  double* dst = P.recv[sel][dst_peer[i]] + ((size_t)dst_conn[i] * qsize + q) * 2 * NLEV;
+  for (int k = threadIdx.x; k < 2 * NLEV; k += blockDim.x) dst[k] = src[k];
+}
+// launched behind the pack kernel on the same stream: its stores are complete; make them visible, then publish
+__global__ void halo_signal_kernel(HaloPeers P, int epoch) {
+  __threadfence_system();
+  if (threadIdx.x < P.npeers) {
+    int* f = P.flags[threadIdx.x] + P.my_rank;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+  }
+}
+__global__ void halo_wait_kernel(const int* flags, HaloPeers P, int epoch) {
+  if (threadIdx.x < P.npeers) {
+    const int* f = flags + P.rank_of[threadIdx.x];
+    int v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    } while (v - epoch < 0);
+  }
+  __threadfence_system();
+}
+
 // min/max: qlim [ie][QSIZE_D][2][NLEV]; halo slot [conn][qsize][2][NLEV]
 __global__ void minmax_pack_kernel(const int* __restrict__ send_elem, const double* __restrict__ qlim, int qsize,
                                    double* __restrict__ buf) {
@@ -325,11 +378,150 @@ void free_exchange_plan() {
   if (S.send_conn_elem) { cudaFree(S.send_conn_elem); S.send_conn_elem = nullptr; }
   if (S.sendbuf) { cudaFree(S.sendbuf); S.sendbuf = nullptr; }
   if (S.recvbuf) { cudaFree(S.recvbuf); S.recvbuf = nullptr; }
+  for (void* m : S.peer_alloc)
+    if (m) cudaIpcCloseMemHandle(m);
+  S.peer_alloc.clear();
+  if (S.halo_alloc) { cudaFree(S.halo_alloc); S.halo_alloc = nullptr; }
+  S.halo_recv[0] = S.halo_recv[1] = nullptr; S.halo_flags = nullptr; S.halo_buf_doubles = 0;
+  if (S.send_pt_dst) { cudaFree(S.send_pt_dst); S.send_pt_dst = nullptr; }
+  if (S.send_pt_peer) { cudaFree(S.send_pt_peer); S.send_pt_peer = nullptr; }
+  if (S.send_conn_dst) { cudaFree(S.send_conn_dst); S.send_conn_dst = nullptr; }
+  if (S.send_conn_peer) { cudaFree(S.send_conn_peer); S.send_conn_peer = nullptr; }
+  S.p2p = false; S.halo_epoch = 0;
   S.nnodes = 0; S.n_halo_pts = S.n_send_pts = S.n_halo_conn = S.n_send_conn = 0;
   // every per-peer table: build_exchange_plan() appends, and halo_sendrecv() indexes them by peer slot
   S.peer.clear();
   S.peer_send_off.clear(); S.peer_send_cnt.clear(); S.peer_recv_off.clear(); S.peer_recv_cnt.clear();
   S.peer_csend_off.clear(); S.peer_csend_cnt.clear(); S.peer_crecv_off.clear(); S.peer_crecv_cnt.clear();
+}
+
+// Receive buffers of a multi-rank session. Collective over the session's ranks (every rank calls it from
+// init_boundary_exchanges_c): the IPC handle of this rank's [recv 0 | recv 1 | flags] allocation and the
+// offsets at which it expects each sender's points are all-gathered, and every neighbour's allocation is
+// mapped. HXX_HALO=nccl (or a failed mapping on any rank) keeps the staged path: pack -> grouped
+// ncclSend/ncclRecv -> receive buffer 0.
+static void setup_halo_buffers(size_t n_send_pts, size_t n_send_conn) {
+#ifdef HXX_WITH_NCCL
+  ncclComm_t comm = (ncclComm_t)S.nccl;
+  if (!comm) runtime_abort("halo exchange: NCCL communicator not initialised", 13);
+  const int R = S.nranks;
+  if ((int)S.peer.size() > MAX_PEERS) runtime_abort("halo exchange: more neighbour ranks than MAX_PEERS", 13);
+  // this rank's needs, and the largest over the ranks (buffers are symmetric per pair, sized per rank)
+  const size_t nd = std::max<size_t>(
+      1, std::max((size_t)std::max(S.n_send_pts, S.n_halo_pts) * MAX_DSS_FIELDS * NLEV,
+                  (size_t)std::max(S.n_send_conn, S.n_halo_conn) * QSIZE_D * 2 * NLEV));
+  S.halo_buf_doubles = nd;
+  const size_t flag_bytes = ((size_t)R * sizeof(int) + 255) / 256 * 256;
+  CUDA_OK(cudaMalloc(&S.halo_alloc, 2 * nd * sizeof(double) + flag_bytes));
+  CUDA_OK(cudaMemset(S.halo_alloc, 0, 2 * nd * sizeof(double) + flag_bytes));
+  S.halo_recv[0] = (double*)S.halo_alloc;
+  S.halo_recv[1] = S.halo_recv[0] + nd;
+  S.halo_flags = (int*)(S.halo_recv[1] + nd);
+  S.recvbuf = nullptr;
+  CUDA_OK(cudaMalloc(&S.sendbuf, nd * sizeof(double)));  // staged (NCCL) path only
+  // record = [IPC handle (64 B) | nd (8 B) | want_p2p (8 B) | recv_off[R] | crecv_off[R]] (ints, -1 = not a neighbour)
+  const size_t rec = 64 + 16 + 2 * (size_t)R * sizeof(int);
+  std::vector<unsigned char> mine(rec, 0), all(rec * R, 0);
+  cudaIpcMemHandle_t hnd;
+  const char* env = std::getenv("HXX_HALO");
+  long long want = !(env && !std::strcmp(env, "nccl"));
+  if (want && cudaIpcGetMemHandle(&hnd, S.halo_alloc) != cudaSuccess) { want = 0; cudaGetLastError(); }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (want) std::memcpy(mine.data(), &hnd, 64);
+  const long long nd_ll = (long long)nd;
+  std::memcpy(mine.data() + 64, &nd_ll, 8);
+  std::memcpy(mine.data() + 72, &want, 8);
+  int* offs = reinterpret_cast<int*>(mine.data() + 80);
+  for (int r = 0; r < 2 * R; ++r) offs[r] = -1;
+  for (size_t j = 0; j < S.peer.size(); ++j) {
+    offs[S.peer[j]] = S.peer_recv_off[j];
+    offs[R + S.peer[j]] = S.peer_crecv_off[j];
+  }
+  unsigned char* d_all = nullptr;
+  CUDA_OK(cudaMalloc(&d_all, rec * R));
+  CUDA_OK(cudaMemcpy(d_all + rec * S.rank, mine.data(), rec, cudaMemcpyHostToDevice));
+  if (ncclAllGather(d_all + rec * S.rank, d_all, rec, ncclChar, comm, S.stream) != ncclSuccess)
+    runtime_abort("halo exchange: ncclAllGather of the IPC handles failed", 1);
+  CUDA_OK(cudaStreamSynchronize(S.stream));
+  CUDA_OK(cudaMemcpy(all.data(), d_all, rec * R, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaFree(d_all));
+  bool p2p = true;
+  for (int r = 0; r < R; ++r) {
+    long long w;
+    std::memcpy(&w, all.data() + rec * r + 72, 8);
+    p2p = p2p && w;
+  }
+  HaloPeers& P = g_peers;
+  P = HaloPeers{};
+  P.npeers = (int)S.peer.size();
+  P.my_rank = S.rank;
+  std::vector<int> dst_off(S.peer.size(), 0), cdst_off(S.peer.size(), 0);
+  S.peer_alloc.assign(S.peer.size(), nullptr);
+  for (size_t j = 0; j < S.peer.size() && p2p; ++j) {
+    const unsigned char* pr = all.data() + rec * S.peer[j];
+    cudaIpcMemHandle_t ph;
+    std::memcpy(&ph, pr, 64);
+    long long pnd;
+    std::memcpy(&pnd, pr + 64, 8);
+    const int* poffs = reinterpret_cast<const int*>(pr + 80);
+    void* base = nullptr;
+    if (cudaIpcOpenMemHandle(&base, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      p2p = false;
+      break;
+    }
+    S.peer_alloc[j] = base;
+    P.recv[0][j] = (double*)base;
+    P.recv[1][j] = (double*)base + pnd;
+    P.flags[j] = (int*)((double*)base + 2 * pnd);
+    P.rank_of[j] = S.peer[j];
+    dst_off[j] = poffs[S.rank];
+    cdst_off[j] = poffs[R + S.rank];
+    if (dst_off[j] < 0 || cdst_off[j] < 0) runtime_abort("halo exchange: a neighbour rank does not list this rank", 13);
+  }
+  // a mapping that failed anywhere sends every rank down the staged path (one more tiny collective)
+  {
+    int* d_ok = nullptr;
+    CUDA_OK(cudaMalloc(&d_ok, sizeof(int)));
+    const int ok = p2p ? 1 : 0;
+    CUDA_OK(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    if (ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm, S.stream) != ncclSuccess)
+      runtime_abort("halo exchange: ncclAllReduce failed", 1);
+    CUDA_OK(cudaStreamSynchronize(S.stream));
+    int okall = 0;
+    CUDA_OK(cudaMemcpy(&okall, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaFree(d_ok));
+    p2p = okall != 0;
+  }
+  S.p2p = p2p;
+  if (S.rank == 0 && std::getenv("HXX_BANNER"))
+    std::printf("HOMMEXX-B200 halo: %s\n", p2p ? "P2P stores over NVLink (CUDA IPC)" : "pack + ncclSend/ncclRecv");
+  if (!p2p) {
+    for (void*& m : S.peer_alloc)
+      if (m) { cudaIpcCloseMemHandle(m); m = nullptr; }
+    return;
+  }
+  // destination tables of the pack kernels
+  std::vector<int> pt_dst(n_send_pts), pt_peer(n_send_pts), c_dst(n_send_conn), c_peer(n_send_conn);
+  for (size_t j = 0; j < S.peer.size(); ++j) {
+    for (int i = 0; i < S.peer_send_cnt[j]; ++i) {
+      pt_dst[S.peer_send_off[j] + i] = dst_off[j] + i;
+      pt_peer[S.peer_send_off[j] + i] = (int)j;
+    }
+    for (int i = 0; i < S.peer_csend_cnt[j]; ++i) {
+      c_dst[S.peer_csend_off[j] + i] = cdst_off[j] + i;
+      c_peer[S.peer_csend_off[j] + i] = (int)j;
+    }
+  }
+  auto up = [](int*& d, const std::vector<int>& h) {
+    CUDA_OK(cudaMalloc(&d, std::max<size_t>(1, h.size()) * sizeof(int)));
+    if (!h.empty()) CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+  };
+  up(S.send_pt_dst, pt_dst); up(S.send_pt_peer, pt_peer); up(S.send_conn_dst, c_dst); up(S.send_conn_peer, c_peer);
+#else
+  (void)n_send_pts; (void)n_send_conn;
+  runtime_abort("halo exchange: built without NCCL", 12);
+#endif
 }
 
 void build_exchange_plan() {
@@ -562,10 +754,8 @@ void build_exchange_plan() {
     CUDA_OK(cudaMemcpy(S.send_src, send_src.data(), send_src.size() * sizeof(int), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMalloc(&S.send_conn_elem, send_conn_elem.size() * sizeof(int)));
     CUDA_OK(cudaMemcpy(S.send_conn_elem, send_conn_elem.data(), send_conn_elem.size() * sizeof(int), cudaMemcpyHostToDevice));
-    const size_t nd = std::max((size_t)S.n_send_pts * MAX_DSS_FIELDS * NLEV, (size_t)S.n_send_conn * QSIZE_D * 2 * NLEV);
-    CUDA_OK(cudaMalloc(&S.sendbuf, nd * sizeof(double)));
-    CUDA_OK(cudaMalloc(&S.recvbuf, nd * sizeof(double)));
   }
+  if (S.nranks > 1) setup_halo_buffers(send_src.size(), snd.size());
 }
 
 // grouped send/recv with every neighbour rank; offsets/counts in units of `unit` doubles
@@ -578,7 +768,7 @@ static void halo_sendrecv(const std::vector<int>& soff, const std::vector<int>& 
   for (size_t i = 0; i < S.peer.size(); ++i) {
     ok = ok && ncclSend(S.sendbuf + (size_t)soff[i] * unit, (size_t)scnt[i] * unit, ncclDouble, S.peer[i], comm,
                         S.comm_stream) == ncclSuccess;
-    ok = ok && ncclRecv(S.recvbuf + (size_t)roff[i] * unit, (size_t)rcnt[i] * unit, ncclDouble, S.peer[i], comm,
+    ok = ok && ncclRecv(S.halo_recv[0] + (size_t)roff[i] * unit, (size_t)rcnt[i] * unit, ncclDouble, S.peer[i], comm,
                         S.comm_stream) == ncclSuccess;
   }
   if (ncclGroupEnd() != ncclSuccess || !ok) runtime_abort("halo exchange: NCCL send/recv failed", 1);
@@ -592,15 +782,48 @@ static void halo_sendrecv(const std::vector<int>& soff, const std::vector<int>& 
 // soon as the producer has finished, while the compute stream does the DSS of every node whose
 // sharers are all on this rank (pair and quad lists — they never touch a packed point); only the
 // generic kernel, which reads the receive buffer, waits for the halo.
+// One halo exchange on the communication stream, behind everything issued so far on the compute stream.
+// Returns the receive buffer the consumer must read once halo_arrived() has been issued on its stream.
+template <class PackP2P, class PackStaged>
+static const double* halo_start(PackP2P&& pack_p2p, PackStaged&& pack_staged) {
+  CUDA_OK(cudaEventRecord(S.ev_produced, S.stream));
+  CUDA_OK(cudaStreamWaitEvent(S.comm_stream, S.ev_produced, 0));
+  ++S.halo_epoch;
+  if (S.p2p) {
+    const int sel = (int)(S.halo_epoch & 1u);
+    pack_p2p(sel);
+    KERNEL_LAUNCHED(K_HALO_PACK);
+    halo_signal_kernel<<<1, 32, 0, S.comm_stream>>>(g_peers, (int)S.halo_epoch);
+    KERNEL_LAUNCHED(K_HALO_PACK);
+    return S.halo_recv[sel];
+  }
+  pack_staged();
+  KERNEL_LAUNCHED(K_HALO_PACK);
+  return S.halo_recv[0];
+}
+static void halo_arrived() {  // on the compute stream, before the first kernel that reads the halo
+  if (S.p2p) {
+    halo_wait_kernel<<<1, 32, 0, S.stream>>>(S.halo_flags, g_peers, (int)S.halo_epoch);
+    KERNEL_LAUNCHED(K_HALO_PACK);
+  } else {
+    CUDA_OK(cudaStreamWaitEvent(S.stream, S.ev_halo, 0));
+  }
+}
+
 void dss_exchange(const FieldList& fl, bool rspheremp) {
   const bool halo = S.n_send_pts > 0;
+  const double* recv = nullptr;
   if (halo) {
-    CUDA_OK(cudaEventRecord(S.ev_produced, S.stream));
-    CUDA_OK(cudaStreamWaitEvent(S.comm_stream, S.ev_produced, 0));
-    halo_pack_kernel<<<dim3(S.n_send_pts, fl.nf), 96, 0, S.comm_stream>>>(S.send_src, S.n_send_pts, fl, S.sendbuf);
-    KERNEL_LAUNCHED(K_HALO_PACK);
-    halo_sendrecv(S.peer_send_off, S.peer_send_cnt, S.peer_recv_off, S.peer_recv_cnt, (size_t)fl.nf * NLEV);
-    CUDA_OK(cudaEventRecord(S.ev_halo, S.comm_stream));
+    recv = halo_start(
+        [&](int sel) {
+          halo_pack_p2p_kernel<<<dim3(S.n_send_pts, fl.nf), 96, 0, S.comm_stream>>>(S.send_src, S.send_pt_dst,
+                                                                                    S.send_pt_peer, fl, g_peers, sel);
+        },
+        [&] {
+          halo_pack_kernel<<<dim3(S.n_send_pts, fl.nf), 96, 0, S.comm_stream>>>(S.send_src, S.n_send_pts, fl, S.sendbuf);
+          halo_sendrecv(S.peer_send_off, S.peer_send_cnt, S.peer_recv_off, S.peer_recv_cnt, (size_t)fl.nf * NLEV);
+          CUDA_OK(cudaEventRecord(S.ev_halo, S.comm_stream));
+        });
   }
   const int ny = (fl.nf + DSS_FPB - 1) / DSS_FPB;
   const bool avg = fl.navg > 0;
@@ -616,13 +839,24 @@ void dss_exchange(const FieldList& fl, bool rspheremp) {
     KERNEL_LAUNCHED(K_DSS);
   };
   DssLists L{(const DssPair*)S.dss_pairs, S.npairs, nblk(S.npairs), (const DssQuad*)S.dss_quads, S.nquads, nblk(S.nquads),
-             S.nodes, halo ? 0 : S.nnodes, S.recvbuf};
+             S.nodes, halo ? 0 : S.nnodes, recv};
   launch(L, L.nb_pair + L.nb_quad + nblk(L.nnodes));
   if (halo) {
-    CUDA_OK(cudaStreamWaitEvent(S.stream, S.ev_halo, 0));
-    DssLists G{nullptr, 0, 0, nullptr, 0, 0, S.nodes, S.nnodes, S.recvbuf};
+    halo_arrived();
+    DssLists G{nullptr, 0, 0, nullptr, 0, 0, S.nodes, S.nnodes, recv};
     launch(G, nblk(S.nnodes));
   }
+}
+
+// Asynchronous NCCL errors (a peer that died) surface here instead of as a hang; polled once per
+// prim_run_subcycle_c, next to the remap's abort flag.
+void check_comm_errors() {
+#ifdef HXX_WITH_NCCL
+  if (!S.nccl) return;
+  ncclResult_t st = ncclSuccess;
+  if (ncclCommGetAsyncError((ncclComm_t)S.nccl, &st) != ncclSuccess || (st != ncclSuccess && st != ncclInProgress))
+    runtime_abort("halo exchange: asynchronous NCCL error (a peer rank failed?)", 1);
+#endif
 }
 
 void scale_interior_rspheremp(const FieldList& fl) {
@@ -636,24 +870,29 @@ void minmax_exchange() {
   const int nq = S.p.qsize;
   if (!S.nelemd || !nq) return;
   const bool halo = S.n_send_conn > 0;
+  const double* recv = nullptr;
   if (halo) {
-    CUDA_OK(cudaEventRecord(S.ev_produced, S.stream));
-    CUDA_OK(cudaStreamWaitEvent(S.comm_stream, S.ev_produced, 0));
-    minmax_pack_kernel<<<dim3(S.n_send_conn, nq), 96, 0, S.comm_stream>>>(S.send_conn_elem, S.qlim, nq, S.sendbuf);
-    KERNEL_LAUNCHED(K_HALO_PACK);
-    halo_sendrecv(S.peer_csend_off, S.peer_csend_cnt, S.peer_crecv_off, S.peer_crecv_cnt, (size_t)nq * 2 * NLEV);
-    CUDA_OK(cudaEventRecord(S.ev_halo, S.comm_stream));
+    recv = halo_start(
+        [&](int sel) {
+          minmax_pack_p2p_kernel<<<dim3(S.n_send_conn, nq), 96, 0, S.comm_stream>>>(
+              S.send_conn_elem, S.send_conn_dst, S.send_conn_peer, S.qlim, nq, g_peers, sel);
+        },
+        [&] {
+          minmax_pack_kernel<<<dim3(S.n_send_conn, nq), 96, 0, S.comm_stream>>>(S.send_conn_elem, S.qlim, nq, S.sendbuf);
+          halo_sendrecv(S.peer_csend_off, S.peer_csend_cnt, S.peer_crecv_off, S.peer_crecv_cnt, (size_t)nq * 2 * NLEV);
+          CUDA_OK(cudaEventRecord(S.ev_halo, S.comm_stream));
+        });
   }
   PROBE(K_MINMAX);
   if (!halo) {
-    minmax_kernel<<<dim3(S.nelemd, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, S.recvbuf, nq, nullptr);
+    minmax_kernel<<<dim3(S.nelemd, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, nullptr, nq, nullptr);
   } else {
     // elements whose eight neighbours are on this rank first, the others once the halo has landed
     if (S.n_interior)
-      minmax_kernel<<<dim3(S.n_interior, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, S.recvbuf, nq, S.elem_order);
-    CUDA_OK(cudaStreamWaitEvent(S.stream, S.ev_halo, 0));
+      minmax_kernel<<<dim3(S.n_interior, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, recv, nq, S.elem_order);
+    halo_arrived();
     if (S.nelemd > S.n_interior)
-      minmax_kernel<<<dim3(S.nelemd - S.n_interior, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, S.recvbuf, nq,
+      minmax_kernel<<<dim3(S.nelemd - S.n_interior, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, recv, nq,
                                                                             S.elem_order + S.n_interior);
   }
   KERNEL_LAUNCHED(K_MINMAX);

@@ -165,6 +165,17 @@ struct Session {
   int n_halo_conn = 0, n_send_conn = 0;  // min/max exchange: one slot per remote connection
   int* send_conn_elem = nullptr;
   std::vector<int> peer_csend_off, peer_csend_cnt, peer_crecv_off, peer_crecv_cnt;
+  // P2P halo (dss.cu): the pack kernels store straight into the neighbour ranks' receive buffers over NVLink
+  // (CUDA IPC mappings) and raise an epoch flag there; `halo_alloc` = [recv 0 | recv 1 | flags] of this rank
+  bool p2p = false;
+  void* halo_alloc = nullptr;
+  size_t halo_buf_doubles = 0;          // doubles per receive buffer
+  double* halo_recv[2] = {nullptr, nullptr};
+  int* halo_flags = nullptr;            // [nranks], written by the peers
+  std::vector<void*> peer_alloc;        // per peer slot: the peer's halo_alloc mapped here
+  int *send_pt_dst = nullptr, *send_pt_peer = nullptr;      // [n_send_pts]: point index in the peer's buffer, peer slot
+  int *send_conn_dst = nullptr, *send_conn_peer = nullptr;  // [n_send_conn]: the same per connection (min/max)
+  unsigned halo_epoch = 0;              // exchanges so far; identical on every rank
   int* invalid_flag = nullptr;   // device flag: negative/NaN thickness in remap
   int* h_invalid = nullptr;      // pinned
   double* diag[8] = {};

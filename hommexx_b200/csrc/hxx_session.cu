@@ -349,7 +349,12 @@ void initialize_hommexx_session(void) {
     runtime_abort(msg, 1);
   }
   CUDA_OK(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
-  CUDA_OK(cudaStreamCreateWithFlags(&S.comm_stream, cudaStreamNonBlocking));
+  {
+    // the halo stream outranks the compute stream: its (small) pack kernels get the next free SM slots
+    int lo = 0, hi = 0;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_OK(cudaStreamCreateWithPriority(&S.comm_stream, cudaStreamNonBlocking, hi));
+  }
   CUDA_OK(cudaEventCreateWithFlags(&S.ev_produced, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&S.ev_halo, cudaEventDisableTiming));
   S.active = true;
