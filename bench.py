@@ -108,6 +108,7 @@ def workload(args, n_gpus):
     ne120 (86 400 elements, homme-ne120-v1.nl) SFC-partitioned over the N GPUs: STRONG scaling over 2/4/8.
     --weak restores the round-1 weak-scaling meshes (~5400 elements per GPU, ne = round(sqrt(900 N)))."""
     from hommexx_b200 import homme
+    from oracle import oraclelib
     if args.ne:
         ne = args.ne
     elif n_gpus == 1:
@@ -161,12 +162,13 @@ def run_reference(args):
     if rank != 0:
         return
     from hommexx_b200 import homme
+    from oracle import oraclelib
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     ne_s = args.ref_ne
     cfg = workload(args, 1)
     scfg = homme.preset("ne30", ne=ne_s, qsize=cfg.qsize)
-    h = homme.Homme(scfg, homme.ORACLE_LIB)
+    h = homme.Homme(scfg, oraclelib.ORACLE_LIB)
     h.init_dycore()
     dyn = scfg.rsplit * scfg.qsplit
     for _ in range(args.warmup):
@@ -232,6 +234,7 @@ def main():
     import numpy as np
     import torch
     from hommexx_b200 import homme
+    from oracle import oraclelib
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -17,7 +17,6 @@ import numpy as np
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 PKG = pathlib.Path(__file__).resolve().parent
 DRIVER_LIB = PKG / "driver" / "libhomme_driver.so"
-ORACLE_LIB = ROOT / "oracle" / "liboracle.so"
 
 
 def cuda_lib_path(nlev: int, qsize_d: int, flavour: str = "") -> pathlib.Path:
@@ -196,14 +195,6 @@ def load_dycore(path) -> C.CDLL:
     lib.hxx_remap_columns.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     for f in ("hxx_euler_reset", "hxx_euler_precompute_divdp", "hommexx_b200_sync", "finalize_hommexx_session"):
         getattr(lib, f).restype = None
-    return lib
-
-
-def load_oracle(nlev: int, qsize_d: int) -> C.CDLL:
-    """TEST INFRASTRUCTURE: the CPU oracle (oracle/liboracle.so)."""
-    lib = load_dycore(ORACLE_LIB)
-    lib.oracle_set_dims.argtypes = [C.c_int, C.c_int]
-    lib.oracle_set_dims(nlev, qsize_d)
     return lib
 
 

@@ -141,15 +141,14 @@ def run(cfg: homme.Config, libpath, nmax: int, held_suarez: bool = False, out=sy
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
     ap.add_argument("namelist")
-    ap.add_argument("--lib", default="cuda", choices=["cuda", "oracle"])
     ap.add_argument("--nmax", type=int, default=0, help="dynamics steps (default: the namelist's nmax, else 12)")
     ap.add_argument("--held-suarez", action="store_true", help="Held-Suarez forcing through f90_push_forcing_to_cxx")
     args = ap.parse_args(argv)
     nl = parse_namelist(open(args.namelist).read())
     cfg = config_from_namelist(nl)
     nmax = args.nmax or int(nl.get("ctl_nl", {}).get("nmax", 12))
-    lib = homme.ORACLE_LIB if args.lib == "oracle" else homme.cuda_lib_path(cfg.nlev, cfg.qsize_d)
-    run(cfg, lib, nmax, args.held_suarez)
+    # the product has one backend: the CUDA library (load_dycore raises if it is not built; no CPU fallback)
+    run(cfg, homme.cuda_lib_path(cfg.nlev, cfg.qsize_d), nmax, args.held_suarez)
 
 
 if __name__ == "__main__":

@@ -18,7 +18,8 @@ def pytest_configure(config):
 def _built():
     """CPU-side artefacts (driver + oracle) are built on demand; the CUDA libs by build()."""
     from hommexx_b200 import homme
-    if not homme.DRIVER_LIB.exists() or not homme.ORACLE_LIB.exists():
+    from oracle import oraclelib
+    if not homme.DRIVER_LIB.exists() or not oraclelib.ORACLE_LIB.exists():
         import __graft_entry__ as g
         g.build_host()
     yield

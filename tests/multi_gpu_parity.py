@@ -20,24 +20,8 @@ ROOT = pathlib.Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--preset", default="ne8")
-    ap.add_argument("--calls", type=int, default=2)
-    args = ap.parse_args()
-    import torch
-    import torch.distributed as dist
-    from hommexx_b200 import homme
-
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local_rank = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-
-    cfg = homme.preset(args.preset, npart=world)
-    cfg.part_id = rank
-    libpath = homme.cuda_lib_path(cfg.nlev, cfg.qsize_d)
-    lib = homme.load_dycore(libpath)
+def new_comm(lib, dist, torch, rank, world, local_rank):
+    """A fresh ncclUniqueId from rank 0 to every rank, then hommexx_b200_set_comm (before the session starts)."""
     idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
         raw = (C.c_ubyte * 128)()
@@ -47,9 +31,22 @@ def main():
     raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
     lib.hommexx_b200_set_comm(rank, world, local_rank, raw)
 
+
+def one_case(preset, over, calls, dist, torch, rank, world, local_rank):
+    """Multi-rank run of `preset`, then the whole mesh on rank 0's GPU alone: every bit must agree."""
+    from hommexx_b200 import homme
+    import distinct_tracers
+
+    cfg = homme.preset(preset, npart=world, **over)
+    cfg.part_id = rank
+    libpath = homme.cuda_lib_path(cfg.nlev, cfg.qsize_d)
+    lib = homme.load_dycore(libpath)
+    new_comm(lib, dist, torch, rank, world, local_rank)
     h = homme.Homme(cfg, libpath)
+    if cfg.qsize > 4:
+        distinct_tracers.install(h)
     h.init_dycore()
-    for _ in range(args.calls):
+    for _ in range(calls):
         h.run_subcycle()
     h.push_results()
     mine = {k: v.copy() for k, v in h.state().items()}  # the views die with the driver
@@ -62,10 +59,12 @@ def main():
     ok = True
     if rank == 0:
         lib.hommexx_b200_set_comm(0, 1, local_rank, None)
-        cfg1 = homme.preset(args.preset, npart=1)
+        cfg1 = homme.preset(preset, npart=1, **over)
         h1 = homme.Homme(cfg1, libpath)
+        if cfg1.qsize > 4:
+            distinct_tracers.install(h1)
         h1.init_dycore()
-        for _ in range(args.calls):
+        for _ in range(calls):
             h1.run_subcycle()
         h1.push_results()
         ref = {k: v.copy() for k, v in h1.state().items()}
@@ -83,13 +82,35 @@ def main():
                     print(f"MISMATCH field {k}: max |diff| = {d:.3e}", flush=True)
                     ok = False
         h1.close()
-        print(f"multi_gpu_parity: {world} ranks, preset {args.preset}, {nel} elements, {args.calls} calls: "
+        print(f"multi_gpu_parity: {world} ranks, preset {preset} {over}, {nel} elements, {calls} calls: "
               f"{'bit-identical to the single-GPU run' if ok else 'FAILED'}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.barrier()
+    return bool(int(flag.item()))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--preset", default="ne8")
+    ap.add_argument("--calls", type=int, default=2)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT / "tests"))
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    ok = True
+    # Three multi-rank sessions in ONE process (a session's halo tables must not leak into the next one): the
+    # 4-tracer build, then the benchmarked (72, 40) build with 40 distinct tracers, then the first one again on a
+    # different mesh.
+    for preset, over in ((args.preset, {}), ("ne8", dict(qsize=40, qsize_d=40)), ("ne4", {})):
+        ok = one_case(preset, over, args.calls, dist, torch, rank, world, local_rank) and ok
     dist.destroy_process_group()
-    sys.exit(0 if int(flag.item()) else 1)
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == "__main__":

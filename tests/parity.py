@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from hommexx_b200 import homme
+from oracle import oraclelib
 
 # every named device array whose meaning is identical in both libraries
 STATE_FIELDS = ["v", "t", "dp3d", "ps_v", "omega_p", "eta_dot_dpdn", "derived_vn0", "derived_dp", "divdp",
@@ -28,7 +29,7 @@ def pair(cfg, init="jw"):
     """(cuda, oracle) Homme objects on identical inputs, both initialised."""
     need_gpu()
     hc = homme.Homme(cfg, cuda_lib(cfg.nlev, cfg.qsize_d), init=init)
-    ho = homme.Homme(cfg, homme.ORACLE_LIB, init=init)
+    ho = homme.Homme(cfg, oraclelib.ORACLE_LIB, init=init)
     hc.init_dycore()
     ho.init_dycore()
     assert hc.lib.hommexx_b200_backend() == b"cuda-sm100a"

@@ -8,6 +8,7 @@ import pytest
 
 import __graft_entry__ as g
 from hommexx_b200 import homme
+from oracle import oraclelib
 
 HEADER = pathlib.Path(__file__).resolve().parents[1] / "include" / "hommexx_b200.h"
 
@@ -42,7 +43,7 @@ def test_cuda_library_exports_every_declared_symbol(variant):
 
 
 def test_oracle_exports_the_same_abi():
-    lib = C.CDLL(str(homme.ORACLE_LIB))
+    lib = C.CDLL(str(oraclelib.ORACLE_LIB))
     for s in declared_symbols():
         if s == "hommexx_b200_nccl_unique_id":
             continue  # multi-GPU wiring exists only in the product

@@ -12,6 +12,7 @@ import pytest
 import abi
 import parity
 from hommexx_b200 import homme
+from oracle import oraclelib
 from limiter_problems import EPS, check_limited, feasible_problem, run_limiter
 
 pytestmark = pytest.mark.gpu
@@ -29,7 +30,7 @@ def cuda():
 
 @pytest.fixture()
 def oracle():
-    lib = homme.load_oracle(NLEV, 4)
+    lib = oraclelib.load_oracle(NLEV, 4)
     yield lib
     lib.finalize_hommexx_session()
 
@@ -103,7 +104,7 @@ def test_limiter_properties_and_oracle_parity(nlev, option):
     parity.need_gpu()
     cu = homme.load_dycore(parity.cuda_lib(nlev, 4))
     cu.initialize_hommexx_session()
-    ora = homme.load_oracle(nlev, 4)
+    ora = oraclelib.load_oracle(nlev, 4)
     rng = np.random.default_rng(9)
     for seed in range(4):
         sph, dpm, pt, ql, mass = feasible_problem(50, nlev, 2000 + seed)
@@ -125,7 +126,7 @@ def test_remap_columns_bitwise(nlev, alg):
     parity.need_gpu()
     cu = homme.load_dycore(parity.cuda_lib(nlev, 4))
     cu.initialize_hommexx_session()
-    ora = homme.load_oracle(nlev, 4)
+    ora = oraclelib.load_oracle(nlev, 4)
     ref_path = pathlib.Path(__file__).resolve().parents[1] / "oracle" / "_ref" / f"libref_remap_{nlev}.so"
     ref = C.CDLL(str(ref_path)) if ref_path.exists() else None
     rng = np.random.default_rng(100 + nlev)

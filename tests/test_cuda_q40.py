@@ -13,6 +13,7 @@ import pytest
 import distinct_tracers
 import parity
 from hommexx_b200 import homme
+from oracle import oraclelib
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-11  # north_star
@@ -25,7 +26,7 @@ def pair40(cfg, flavour=""):
     if not path.exists():
         raise RuntimeError(f"{path} is not built; the CUDA dycore has no fallback. Run __graft_entry__.build().")
     hc = homme.Homme(cfg, path)
-    ho = homme.Homme(cfg, homme.ORACLE_LIB)
+    ho = homme.Homme(cfg, oraclelib.ORACLE_LIB)
     for h in (hc, ho):
         q = distinct_tracers.install(h)
         h.init_dycore()

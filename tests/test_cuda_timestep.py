@@ -7,6 +7,7 @@ import pytest
 
 import parity
 from hommexx_b200 import homme
+from oracle import oraclelib
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-11  # north_star
@@ -198,7 +199,7 @@ def test_dcmip11_tracer_stress_parity(preset, calls):
     cfg = homme.preset("ne30", qsize=4, qsize_d=4) if preset == "ne30q4" else homme.preset(preset)
     parity.need_gpu()
     hc = homme.Homme(cfg, parity.cuda_lib(cfg.nlev, cfg.qsize_d))
-    ho = homme.Homme(cfg, homme.ORACLE_LIB)
+    ho = homme.Homme(cfg, oraclelib.ORACLE_LIB)
     for h in (hc, ho):
         dcmip_tracers.install(h)
         h.init_dycore()

@@ -16,12 +16,13 @@ def _rank_main(rank, world, port, ne, q):
     import torch.distributed as dist
     sys.path.insert(0, str(ROOT))
     from hommexx_b200 import homme
+    from oracle import oraclelib
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         cfg = homme.preset("ne4", ne=ne, npart=world)
         cfg.part_id = rank
-        h = homme.Homme(cfg, homme.ORACLE_LIB)  # driver only: no dycore call is made
+        h = homme.Homme(cfg, oraclelib.ORACLE_LIB)  # driver only: no dycore call is made
         gids = h.local_gids()
         conn = h.connections()                  # (lid1,gid1,pos1,pid1, lid2,gid2,pos2,pid2), all 1-based
         sph = h.array("spheremp").copy()
@@ -91,11 +92,12 @@ def test_partition_properties_many_parts(ne, npart):
     genspacepart (spacecurve_mod.F90:1232-1264), parts spatially compact (at most two edge-connected patches and a
     perimeter-sized halo), and every off-rank connection mirrored by the owner."""
     from hommexx_b200 import homme
+    from oracle import oraclelib
     parts = []
     for r in range(npart):
         cfg = homme.preset("ne4", ne=ne, npart=npart)
         cfg.part_id = r
-        h = homme.Homme(cfg, homme.ORACLE_LIB)
+        h = homme.Homme(cfg, oraclelib.ORACLE_LIB)
         parts.append((h.local_gids(), h.connections(), float(h.array("spheremp").sum())))
         nelem = h.nelem
         h.close()

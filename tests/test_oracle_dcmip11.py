@@ -5,6 +5,7 @@ compare with (cxx_f90_interface.cpp:44), so the checks are the case's own invari
 import numpy as np
 
 from hommexx_b200 import dcmip, homme
+from oracle import oraclelib
 
 
 def test_initial_fields_follow_the_dcmip_definition():
@@ -25,7 +26,7 @@ def test_initial_fields_follow_the_dcmip_definition():
 
 
 def test_one_day_of_deformational_flow():
-    d = dcmip.Dcmip11(8, 26, homme.ORACLE_LIB, tstep=600.0)
+    d = dcmip.Dcmip11(8, 26, oraclelib.ORACLE_LIB, tstep=600.0)
     m0, q0 = d.masses(), d.q()
     for _ in range(144):
         d.step()

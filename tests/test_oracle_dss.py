@@ -7,12 +7,13 @@ import numpy as np
 import pytest
 
 from hommexx_b200 import homme
+from oracle import oraclelib
 
 
 @pytest.fixture(scope="module")
 def sess():
     cfg = homme.preset("ne4", ne=3, nlev=8, qsize=2, qsize_d=2, vcoord="")
-    h = homme.Homme(cfg, homme.ORACLE_LIB)
+    h = homme.Homme(cfg, oraclelib.ORACLE_LIB)
     h.init_dycore()
     yield h
     h.close()

@@ -6,6 +6,7 @@ import pytest
 
 from forcing_inputs import fill_forcing
 from hommexx_b200 import homme
+from oracle import oraclelib
 
 CP, CPWV = 1005.0, 1870.0
 
@@ -19,7 +20,7 @@ def _dp(h, ps):
 @pytest.mark.parametrize("moist,ftype", [(0, 0), (1, 0), (0, 2)])
 def test_forcing_matches_formulas(moist, ftype):
     cfg = homme.preset("ne4", nlev=26, vcoord="cam-26", moisture=moist, ftype=ftype)
-    h = homme.Homme(cfg, homme.ORACLE_LIB)
+    h = homme.Homme(cfg, oraclelib.ORACLE_LIB)
     h.init_dycore()
     fill_forcing(h)
     st0 = {k: v.copy() for k, v in h.state().items()}
@@ -65,7 +66,7 @@ def test_forcing_matches_formulas(moist, ftype):
 
 def test_forcing_roundtrip_and_qdp_push():
     cfg = homme.preset("ne4", nlev=26, vcoord="cam-26")
-    h = homme.Homme(cfg, homme.ORACLE_LIB)
+    h = homme.Homme(cfg, oraclelib.ORACLE_LIB)
     h.init_dycore()
     fill_forcing(h)
     f = {k: v.copy() for k, v in h.forcing().items()}
@@ -84,7 +85,7 @@ def test_forcing_roundtrip_and_qdp_push():
 @pytest.mark.parametrize("cpstar", [0, 1])
 def test_diagnostics_match_formulas(cpstar):
     cfg = homme.preset("ne4", nlev=26, vcoord="cam-26", disable_diagnostics=0, use_cpstar=cpstar, state_frequency=3)
-    h = homme.Homme(cfg, homme.ORACLE_LIB)
+    h = homme.Homme(cfg, oraclelib.ORACLE_LIB)
     h.init_dycore()
     st0 = {k: v.copy() for k, v in h.state().items()}
     _, _, n0, _ = h.time_levels()

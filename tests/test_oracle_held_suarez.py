@@ -3,7 +3,9 @@ driving the oracle through f90_push_forcing_to_cxx + prim_run_subcycle_c (ftype 
 import numpy as np
 
 from hommexx_b200 import held_suarez as hs
+from oracle import oraclelib
 from hommexx_b200 import homme
+from oracle import oraclelib
 
 
 def test_forcing_formulas():
@@ -29,7 +31,7 @@ def test_held_suarez_forced_run_on_the_oracle():
     cfg = homme.preset("prtcA", qsize=0, ftype=0)
     runs = {}
     for forced in (False, True):
-        h = homme.Homme(cfg, homme.ORACLE_LIB)
+        h = homme.Homme(cfg, oraclelib.ORACLE_LIB)
         h.init_dycore()
         for _ in range(6):
             if forced:

@@ -8,13 +8,14 @@ import time
 import numpy as np
 
 from hommexx_b200 import homme
+from oracle import oraclelib
 
 
 def _drift(ne):
     s = (4.0 / ne)
     nu = 7e15 * s ** 3.2
     cfg = homme.preset("prtcA", ne=ne, qsize=0, u_perturb=0.0, tstep=600.0 * s, nu=nu, nu_p=nu, nu_div=nu)
-    h = homme.Homme(cfg, homme.ORACLE_LIB)
+    h = homme.Homme(cfg, oraclelib.ORACLE_LIB)
     h.init_dycore()
     s0 = {k: v.copy() for k, v in h.state().items()}
     for _ in range(4 * ne // 4):      # 2 simulated hours

@@ -5,13 +5,14 @@ import numpy as np
 import pytest
 
 from hommexx_b200 import homme
+from oracle import oraclelib
 from limiter_problems import EPS, check_limited, feasible_problem, run_limiter
 
 
 @pytest.mark.parametrize("nlev", [72, 26])
 @pytest.mark.parametrize("option", [8, 9])
 def test_limiter_bounds_and_mass(nlev, option):
-    lib = homme.load_oracle(nlev, 4)
+    lib = oraclelib.load_oracle(nlev, 4)
     for seed in range(4):
         sph, dpm, pt, ql, mass = feasible_problem(6, nlev, 1000 + seed)
         out, ql_out = run_limiter(lib, option, sph, dpm, pt, ql)
@@ -21,7 +22,7 @@ def test_limiter_bounds_and_mass(nlev, option):
 
 def test_limiter_is_identity_inside_bounds():
     nlev = 26
-    lib = homme.load_oracle(nlev, 4)
+    lib = oraclelib.load_oracle(nlev, 4)
     sph, dpm, _, ql, _ = feasible_problem(3, nlev, 5)
     pt = np.random.default_rng(5).uniform(0.1, 0.9, dpm.shape) * dpm
     ql[:, 0] = 0.0; ql[:, 1] = 10.0
@@ -33,7 +34,7 @@ def test_limiter_is_identity_inside_bounds():
 def test_limiter_relaxes_infeasible_bounds_and_clamps_negative_min():
     """EulerStepFunctorImpl.hpp:729-742: qmin<0 -> 0; bounds relaxed to the mean when infeasible."""
     nlev = 8
-    lib = homme.load_oracle(nlev, 4)
+    lib = oraclelib.load_oracle(nlev, 4)
     rng = np.random.default_rng(3)
     sph = rng.uniform(1 / 16, 2 / 16, (1, 16)); dpm = rng.uniform(0.5, 1.0, (1, 16, nlev))
     pt = rng.uniform(0.4, 0.6, (1, 16, nlev)) * dpm
@@ -50,7 +51,7 @@ def test_lim8_vs_caas_one_norm():
     """preqx_ut.cpp:1483-1531: both limiters solve the same problem; lim8's 1-norm change is not larger
     than CAAS's by more than round-off."""
     nlev = 26
-    lib = homme.load_oracle(nlev, 4)
+    lib = oraclelib.load_oracle(nlev, 4)
     sph, dpm, pt, ql, mass = feasible_problem(8, nlev, 77)
     o8, _ = run_limiter(lib, 8, sph, dpm, pt, ql)
     o9, _ = run_limiter(lib, 9, sph, dpm, pt, ql)

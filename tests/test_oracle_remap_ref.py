@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from hommexx_b200 import homme
+from oracle import oraclelib
 
 REF_DIR = pathlib.Path(__file__).resolve().parents[1] / "oracle" / "_ref"
 
@@ -36,7 +37,7 @@ def _problem(nlev, qsize, seed):
 @pytest.mark.parametrize("alg", [1, 2])
 def test_remap_bitwise_vs_reference_twin(nlev, alg):
     ref = _ref(nlev)
-    ora = homme.load_oracle(nlev, 4)
+    ora = oraclelib.load_oracle(nlev, 4)
     for seed in range(3):
         qsize = 5
         dp1, dp2, q = _problem(nlev, qsize, 100 * nlev + seed)
@@ -55,7 +56,7 @@ def test_remap_bitwise_vs_reference_twin(nlev, alg):
 
 def test_remap_identity_when_grids_match():
     nlev = 26
-    ora = homme.load_oracle(nlev, 4)
+    ora = oraclelib.load_oracle(nlev, 4)
     dp1, _, q = _problem(nlev, 3, 7)
     src = np.ascontiguousarray(dp1.reshape(nlev, 16).T)
     f = np.ascontiguousarray(q.reshape(3, nlev, 16).transpose(0, 2, 1))

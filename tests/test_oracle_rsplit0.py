@@ -5,11 +5,12 @@ simulated time, and the Eulerian path must conserve tracer mass to round-off."""
 import numpy as np
 
 from hommexx_b200 import homme
+from oracle import oraclelib
 
 
 def _run(rsplit, calls):
     cfg = homme.preset("ne4", rsplit=rsplit)
-    h = homme.Homme(cfg, homme.ORACLE_LIB)
+    h = homme.Homme(cfg, oraclelib.ORACLE_LIB)
     h.init_dycore()
     sph = h.array("spheremp").reshape(-1, 1, 1, 4, 4).copy()
     m0 = (h.state()["Qdp"][:, 0] * sph).sum(axis=(0, 2, 3, 4))

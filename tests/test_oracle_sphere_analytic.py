@@ -7,13 +7,14 @@ import pytest
 
 import abi
 from hommexx_b200 import homme
+from oracle import oraclelib
 
 A = 6.376e6
 NLEV = 26
 
 
 def _mesh(ne):
-    h = homme.Homme(homme.preset("prtcA", ne=ne, qsize=0), homme.ORACLE_LIB)
+    h = homme.Homme(homme.preset("prtcA", ne=ne, qsize=0), oraclelib.ORACLE_LIB)
     h.init_dycore()
     n = h.nelemd
     return h, h.array("lat").reshape(n, 16).copy(), h.array("lon").reshape(n, 16).copy()

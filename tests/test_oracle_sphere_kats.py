@@ -11,6 +11,7 @@ import pytest
 
 import abi
 from hommexx_b200 import homme
+from oracle import oraclelib
 
 KATS = json.loads((pathlib.Path(__file__).parent / "golden" / "sphere_kats.json").read_text())
 NLEV = 8
@@ -18,7 +19,7 @@ NLEV = 8
 
 @pytest.fixture()
 def lib():
-    lib = homme.load_oracle(NLEV, 4)
+    lib = oraclelib.load_oracle(NLEV, 4)
     yield lib
     lib.finalize_hommexx_session()
 
@@ -69,7 +70,7 @@ def test_vorticity_sphere_kat(lib):
 
 def test_dvv_matches_reference_table():
     """The driver's GLL derivative matrix equals the deriv_Dvv block printed by the reference."""
-    h = homme.Homme(homme.preset("ne4", ne=2), homme.ORACLE_LIB, init="none")
+    h = homme.Homme(homme.preset("ne4", ne=2), oraclelib.ORACLE_LIB, init="none")
     dvv = h.array("dvv").copy()
     h.close()
     assert np.abs(dvv - np.asarray(KATS["gradient"]["deriv_Dvv"])).max() < 4e-16

@@ -6,10 +6,11 @@ close — and must not be the same arithmetic."""
 import numpy as np
 
 from hommexx_b200 import homme
+from oracle import oraclelib
 
 
 def _run(cfg, calls=4):
-    h = homme.Homme(cfg, homme.ORACLE_LIB)
+    h = homme.Homme(cfg, oraclelib.ORACLE_LIB)
     h.init_dycore()
     tv = h.array("tensorvisc").copy()
     for _ in range(calls):

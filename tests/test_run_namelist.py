@@ -6,6 +6,7 @@ import pathlib
 import numpy as np
 
 from hommexx_b200 import homme, run
+from oracle import oraclelib
 
 NL = pathlib.Path(run.__file__).parent / "namelists"
 
@@ -30,7 +31,7 @@ def test_prtcA_run_prints_conserved_integrals():
     nl = run.parse_namelist((NL / "prtcA-r3-dry.nl").read_text())
     cfg = run.config_from_namelist(nl)
     buf = io.StringIO()
-    hist = run.run(cfg, homme.ORACLE_LIB, nmax=12, out=buf)
+    hist = run.run(cfg, oraclelib.ORACLE_LIB, nmax=12, out=buf)
     assert [h["nstep"] for h in hist] == [3, 6, 9, 12]
     text = buf.getvalue()
     assert "TOTE" in text and "Q1  mass" in text
