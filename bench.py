@@ -195,10 +195,13 @@ def run_reference(args):
     emit(out)
 
 
+PINNED = []   # host pointers currently page-locked with cudaHostRegister
+
+
 def pin_driver_arrays(h, torch):
     """Page-lock the driver's Fortran-layout arrays so the e2e copies run from pinned memory."""
     rt = torch.cuda.cudart()
-    pinned = []
+    pinned = PINNED
     names = ("v", "T", "dp3d", "Qdp", "Q", "ps_v", "omega_p")
     if sum(h.array(n).nbytes for n in names) > (32 << 30):
         return pinned   # ne120 shards: tens of GB per rank; page-locking that much is slow and can fail
@@ -388,7 +391,8 @@ def main():
     if not args.no_e2e and n_gpus == 1:
         for name in ("FM", "FT", "FQ"):
             a = h.array(name)
-            torch.cuda.cudart().cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+            if int(torch.cuda.cudart().cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0:
+                PINNED.append(a.ctypes.data)
         fo = h.forcing()
         nrep = max(2, min(5, args.steps))
         h2d_c = sum(fo[k].nbytes for k in ("FM", "FT", "FQ"))
@@ -407,10 +411,18 @@ def main():
                        "what": "per call: f90_push_forcing_to_cxx + prim_run_subcycle_c + cxx_push_results_to_f90 "
                                "(prim_driver_mod.F90:1322-1404, the pattern of a CAM-coupled run); PCIe-bound"}
 
+    def unpin_all():
+        # the driver frees its arrays on close: a registration left behind would poison the next allocation that
+        # lands on the same virtual addresses (cudaMemcpyAsync: invalid argument)
+        rt = torch.cuda.cudart()
+        while PINNED:
+            rt.cudaHostUnregister(PINNED.pop())
+
     # ---- the FMA-contracted build of the same sources (parity <= 1e-11, tests/test_cuda_q40.py) ----
     fma = None
     fma_path = homme.cuda_lib_path(cfg.nlev, cfg.qsize_d, "fma")
     if not args.no_fma and n_gpus == 1 and fma_path.exists():
+        unpin_all()
         h.close()
         h = None
         hf = homme.Homme(cfg, fma_path)
@@ -472,6 +484,7 @@ def main():
                "e2e": e2e, "e2e_coupled": e2e_coupled, "fma_build": fma, "cpu_baseline": cpu, "breakdown": breakdown}
         emit(out)
     if h is not None:
+        unpin_all()
         h.close()
     if dist is not None:
         dist.barrier()

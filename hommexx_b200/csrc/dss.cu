@@ -40,19 +40,38 @@ constexpr int DSS_FPB = 8;                           // fields per thread (grid.
 #ifndef HXX_DSS_QUAD_UB
 #define HXX_DSS_QUAD_UB 2
 #endif
-#ifndef HXX_DSS_FB
-#define HXX_DSS_FB 1
-#endif
 #ifndef HXX_DSS_MINB
 #define HXX_DSS_MINB 5
 #endif
-constexpr int DSS_FB = HXX_DSS_FB;  // fields whose loads are in flight together in one thread
+constexpr int DSS_TPB = 128;
 
+// A thread owns DSS_V consecutive levels of its node (16-byte loads and stores: a column is NLEV * 8 bytes, so
+// every even level is 16-byte aligned): the same number of memory instructions and address registers keeps
+// twice the bytes in flight, which is what a pass with no arithmetic to hide its latency behind needs.
+constexpr int DSS_V = (NLEV % 2 == 0) ? 2 : 1;
+constexpr int DSS_NLV = NLEV / DSS_V;  // level groups per node
+struct DV { double v[DSS_V]; };
+__device__ __forceinline__ DV ldv(const double* p) {
+  DV r;
+  if constexpr (DSS_V == 2) {
+    const double2 t = *reinterpret_cast<const double2*>(p);
+    r.v[0] = t.x; r.v[1] = t.y;
+  } else {
+    r.v[0] = *p;
+  }
+  return r;
+}
+__device__ __forceinline__ void stv(double* p, const DV& x) {
+  if constexpr (DSS_V == 2) *reinterpret_cast<double2*>(p) = make_double2(x.v[0], x.v[DSS_V - 1]);
+  else *p = x.v[0];
+}
+
+// Generic nodes: any number of sharers up to four, any of them in the halo, explicit summation orders.
 template <bool RSP, bool AVG>
 __device__ __forceinline__ void dss_nodes_body(const DssNode* __restrict__ nodes, int nnodes, const FieldList& fl,
                                                const double* __restrict__ geo, const double* __restrict__ halo,
                                                long long g, int ychunk) {
-  const int node = (int)(g / NLEV), k = (int)(g % NLEV);
+  const int node = (int)(g / DSS_NLV), k = (int)(g % DSS_NLV) * DSS_V;
   if (node >= nnodes) return;
   const DssNode nd = nodes[node];
   double rs[4];
@@ -60,49 +79,48 @@ __device__ __forceinline__ void dss_nodes_body(const DssNode* __restrict__ nodes
   for (int m = 0; m < 4; ++m)
     rs[m] = (RSP && m < nd.nmem && nd.src[m] >= 0) ? __ldg(geo + (size_t)nd.src[m] * GEO_N + G_RSPHEREMP) : 1.0;
   const int f0 = ychunk * DSS_FPB, f1 = min(fl.nf, f0 + DSS_FPB);
-  for (int fb = f0; fb < f1; fb += DSS_FB) {
-    // the loads of DSS_FB fields are issued before the first store (the fields may alias as far
-    // as the compiler knows, which would otherwise serialise load -> store -> load)
-    double val[DSS_FB][4], avg[DSS_FB][4];
-    double* ptr[DSS_FB][4];
+  for (int f = f0; f < f1; ++f) {
+    // every load is issued before the first store (the fields may alias as far as the compiler knows,
+    // which would otherwise serialise load -> store -> load)
+    DV val[4], avg[4];
+    double* ptr[4];
+    double* base = fl.base[f];
+    const long long es = fl.estride[f];
 #pragma unroll
-    for (int j = 0; j < DSS_FB; ++j) {
-      const int f = min(fb + j, f1 - 1);
-      double* base = fl.base[f];
-      const long long es = fl.estride[f];
+    for (int m = 0; m < 4; ++m) {
+      ptr[m] = nullptr;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        val[j][m] = 0.0;
-        avg[j][m] = 0.0;
-        ptr[j][m] = nullptr;
-        if (m < nd.nmem) {
-          const int s = nd.src[m];
-          if (s >= 0) {
-            ptr[j][m] = base + (size_t)(s >> 4) * es + (s & 15) * NLEV + k;
-            val[j][m] = *ptr[j][m];
-            avg[j][m] = (AVG && f < fl.navg) ? ptr[j][m][fl.avg_delta] : 0.0;
-          } else {
-            val[j][m] = halo[((size_t)(~s) * fl.nf + f) * NLEV + k];
-          }
+      for (int i = 0; i < DSS_V; ++i) { val[m].v[i] = 0.0; avg[m].v[i] = 0.0; }
+      if (m < nd.nmem) {
+        const int s = nd.src[m];
+        if (s >= 0) {
+          ptr[m] = base + (size_t)(s >> 4) * es + (s & 15) * NLEV + k;
+          val[m] = ldv(ptr[m]);
+          if (AVG && f < fl.navg) avg[m] = ldv(ptr[m] + fl.avg_delta);
+        } else {
+          val[m] = ldv(halo + ((size_t)(~s) * fl.nf + f) * NLEV + k);
         }
       }
     }
 #pragma unroll
-    for (int j = 0; j < DSS_FB; ++j) {
-      if (fb + j >= f1) break;
+    for (int m = 0; m < 4; ++m) {
+      if (ptr[m]) {
+        DV acc = val[m];
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        if (ptr[j][m]) {
-          double acc = val[j][m];
+        for (int t = 0; t < 3; ++t) {
+          const int o = nd.ord[m][t];
+          if (o < 4) {
 #pragma unroll
-          for (int t = 0; t < 3; ++t) {
-            const int o = nd.ord[m][t];
-            if (o < 4) acc += o == 0 ? val[j][0] : o == 1 ? val[j][1] : o == 2 ? val[j][2] : val[j][3];
+            for (int i = 0; i < DSS_V; ++i)
+              acc.v[i] += o == 0 ? val[0].v[i] : o == 1 ? val[1].v[i] : o == 2 ? val[2].v[i] : val[3].v[i];
           }
-          if (RSP) acc *= rs[m];
-          if (AVG && fb + j < fl.navg) acc = (avg[j][m] + 2.0 * acc) / 3.0;  // qdp_time_avg, EulerStepFunctorImpl.hpp:379-403
-          *ptr[j][m] = acc;
         }
+#pragma unroll
+        for (int i = 0; i < DSS_V; ++i) {
+          if (RSP) acc.v[i] *= rs[m];
+          if (AVG && f < fl.navg) acc.v[i] = (avg[m].v[i] + 2.0 * acc.v[i]) / 3.0;  // qdp_time_avg, EulerStepFunctorImpl.hpp:379-403
+        }
+        stv(ptr[m], acc);
       }
     }
   }
@@ -110,9 +128,9 @@ __device__ __forceinline__ void dss_nodes_body(const DssNode* __restrict__ nodes
 
 // ---- lean paths -------------------------------------------------------------------------------
 // 80 % of the boundary nodes are edge nodes with two on-rank sharers and nearly all the others
-// are regular element corners with four: they get branch-free kernels with a handful of
+// are regular element corners with four: they get branch-free code with a handful of
 // instructions per (node, level, field). What is left (cube vertices with three sharers, nodes
-// with a sharer on another rank) goes through the generic kernel above.
+// with a sharer on another rank) goes through the generic body above.
 //
 // Pair: both results are a + b (addition commutes, so the reference's "own value first" order
 // gives the same bits for both members).
@@ -124,12 +142,11 @@ __device__ __forceinline__ void dss_nodes_body(const DssNode* __restrict__ nodes
 struct DssPair { int a, b; };
 struct DssQuad { int m[4]; int swaps; int pad[3]; };
 static_assert(sizeof(DssQuad) == 32, "DssQuad layout");
-constexpr int DSS_TPB = 128;
 
 template <bool RSP, bool AVG>
 __device__ __forceinline__ void dss_pair_body(const DssPair* __restrict__ pairs, int npairs, const FieldList& fl,
                                               const double* __restrict__ geo, long long g, int ychunk) {
-  const int ip = (int)(g / NLEV), k = (int)(g % NLEV);
+  const int ip = (int)(g / DSS_NLV), k = (int)(g % DSS_NLV) * DSS_V;
   if (ip >= npairs) return;
   const DssPair pr = pairs[ip];
   const long long ea = pr.a >> 4, eb = pr.b >> 4;
@@ -143,7 +160,7 @@ __device__ __forceinline__ void dss_pair_body(const DssPair* __restrict__ pairs,
   constexpr int UB = HXX_DSS_PAIR_UB;  // fields whose loads are issued before the first store
   for (int fb = f0; fb < f1; fb += UB) {
     double *pa[UB], *pb[UB];
-    double va[UB], vb[UB], qa[UB], qb[UB];
+    DV va[UB], vb[UB], qa[UB], qb[UB];
 #pragma unroll
     for (int j = 0; j < UB; ++j) {
       const int f = min(fb + j, f1 - 1);
@@ -151,25 +168,29 @@ __device__ __forceinline__ void dss_pair_body(const DssPair* __restrict__ pairs,
       const long long es = fl.estride[f];
       pa[j] = base + ea * es + ca;
       pb[j] = base + eb * es + cb;
-      va[j] = *pa[j];
-      vb[j] = *pb[j];
+      va[j] = ldv(pa[j]);
+      vb[j] = ldv(pb[j]);
       if (AVG) {
-        qa[j] = f < fl.navg ? pa[j][fl.avg_delta] : 0.0;
-        qb[j] = f < fl.navg ? pb[j][fl.avg_delta] : 0.0;
+        if (f < fl.navg) { qa[j] = ldv(pa[j] + fl.avg_delta); qb[j] = ldv(pb[j] + fl.avg_delta); }
+        else { qa[j] = va[j]; qb[j] = vb[j]; }
       }
     }
 #pragma unroll
     for (int j = 0; j < UB; ++j) {
       if (fb + j < f1) {
-        const double s = va[j] + vb[j];
-        double xa = s, xb = s;
-        if (RSP) { xa = s * ra; xb = s * rb; }
-        if (AVG && fb + j < fl.navg) {  // qdp_time_avg, EulerStepFunctorImpl.hpp:379-403
-          xa = (qa[j] + 2.0 * xa) / 3.0;
-          xb = (qb[j] + 2.0 * xb) / 3.0;
+        DV xa, xb;
+#pragma unroll
+        for (int i = 0; i < DSS_V; ++i) {
+          const double s = va[j].v[i] + vb[j].v[i];
+          xa.v[i] = s; xb.v[i] = s;
+          if (RSP) { xa.v[i] = s * ra; xb.v[i] = s * rb; }
+          if (AVG && fb + j < fl.navg) {  // qdp_time_avg, EulerStepFunctorImpl.hpp:379-403
+            xa.v[i] = (qa[j].v[i] + 2.0 * xa.v[i]) / 3.0;
+            xb.v[i] = (qb[j].v[i] + 2.0 * xb.v[i]) / 3.0;
+          }
         }
-        *pa[j] = xa;
-        *pb[j] = xb;
+        stv(pa[j], xa);
+        stv(pb[j], xb);
       }
     }
   }
@@ -178,7 +199,7 @@ __device__ __forceinline__ void dss_pair_body(const DssPair* __restrict__ pairs,
 template <bool RSP, bool AVG>
 __device__ __forceinline__ void dss_quad_body(const DssQuad* __restrict__ quads, int nquads, const FieldList& fl,
                                               const double* __restrict__ geo, long long g, int ychunk) {
-  const int iq = (int)(g / NLEV), k = (int)(g % NLEV);
+  const int iq = (int)(g / DSS_NLV), k = (int)(g % DSS_NLV) * DSS_V;
   if (iq >= nquads) return;
   const DssQuad qd = quads[iq];
   long long e[4];
@@ -195,7 +216,7 @@ __device__ __forceinline__ void dss_quad_body(const DssQuad* __restrict__ quads,
   constexpr int UB = HXX_DSS_QUAD_UB;
   for (int fb = f0; fb < f1; fb += UB) {
     double* ptr[UB][4];
-    double v[UB][4], qa[UB][4];
+    DV v[UB][4], qa[UB][4];
 #pragma unroll
     for (int j = 0; j < UB; ++j) {
       const int f = min(fb + j, f1 - 1);
@@ -204,54 +225,67 @@ __device__ __forceinline__ void dss_quad_body(const DssQuad* __restrict__ quads,
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         ptr[j][m] = base + e[m] * es + c[m];
-        v[j][m] = *ptr[j][m];
-        if (AVG) qa[j][m] = f < fl.navg ? ptr[j][m][fl.avg_delta] : 0.0;
+        v[j][m] = ldv(ptr[j][m]);
+        if (AVG) qa[j][m] = f < fl.navg ? ldv(ptr[j][m] + fl.avg_delta) : v[j][m];
       }
     }
 #pragma unroll
     for (int j = 0; j < UB; ++j) {
       if (fb + j < f1) {
-        const double v0 = v[j][0], v1 = v[j][1], v2 = v[j][2], v3 = v[j][3];
-        double x[4];
-        x[0] = ((v0 + v2) + v1) + v3;
-        x[1] = s1 ? ((v1 + v0) + v3) + v2 : ((v1 + v3) + v0) + v2;
-        x[2] = s2 ? ((v2 + v3) + v0) + v1 : ((v2 + v0) + v3) + v1;
-        x[3] = s3 ? ((v3 + v2) + v1) + v0 : ((v3 + v1) + v2) + v0;
+        DV x[4];
+#pragma unroll
+        for (int i = 0; i < DSS_V; ++i) {
+          const double v0 = v[j][0].v[i], v1 = v[j][1].v[i], v2 = v[j][2].v[i], v3 = v[j][3].v[i];
+          x[0].v[i] = ((v0 + v2) + v1) + v3;
+          x[1].v[i] = s1 ? ((v1 + v0) + v3) + v2 : ((v1 + v3) + v0) + v2;
+          x[2].v[i] = s2 ? ((v2 + v3) + v0) + v1 : ((v2 + v0) + v3) + v1;
+          x[3].v[i] = s3 ? ((v3 + v2) + v1) + v0 : ((v3 + v1) + v2) + v0;
+        }
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          double r = x[m];
-          if (RSP) r *= rs[m];
-          if (AVG && fb + j < fl.navg) r = (qa[j][m] + 2.0 * r) / 3.0;
-          *ptr[j][m] = r;
+          DV r = x[m];
+#pragma unroll
+          for (int i = 0; i < DSS_V; ++i) {
+            if (RSP) r.v[i] *= rs[m];
+            if (AVG && fb + j < fl.navg) r.v[i] = (qa[j][m].v[i] + 2.0 * r.v[i]) / 3.0;
+          }
+          stv(ptr[j][m], r);
         }
       }
     }
   }
 }
 
-// One launch per exchange: blocks [0, nb_pair) take the pair list, the next nb_quad blocks the quad list and
-// the rest the generic nodes (the split is block-uniform, so nothing diverges). On several ranks the generic
-// nodes read the halo and are launched on their own once it has landed (nb_node = 0 here).
+// PARTS selects what a launch covers: 1 = the pair list, 2 = the quad list, 4 = the generic nodes; the lists
+// present are consecutive block ranges (the split is block-uniform, so nothing diverges). Pairs are a launch of
+// their own — their body needs far fewer registers, and a pass this latency-bound lives on resident warps; the
+// few generic nodes of a single-rank run ride with the quads, on several ranks they wait for the halo.
 struct DssLists {
   const DssPair* pairs; int npairs, nb_pair;
   const DssQuad* quads; int nquads, nb_quad;
   const DssNode* nodes; int nnodes;
   const double* halo;
 };
-template <bool RSP, bool AVG>
-__global__ void __launch_bounds__(DSS_TPB, HXX_DSS_MINB) dss_kernel(DssLists L, FieldList fl, const double* __restrict__ geo) {
+template <int PARTS, bool RSP, bool AVG>
+__global__ void __launch_bounds__(DSS_TPB, PARTS == 1 ? (AVG ? 4 : 8) : (AVG ? 4 : HXX_DSS_MINB)) dss_kernel(DssLists L, FieldList fl,
+                                                                                    const double* __restrict__ geo) {
   int b = blockIdx.x;
-  if (b < L.nb_pair) {
-    dss_pair_body<RSP, AVG>(L.pairs, L.npairs, fl, geo, (long long)b * DSS_TPB + threadIdx.x, blockIdx.y);
-    return;
+  if constexpr (PARTS & 1) {
+    if (b < L.nb_pair) {
+      dss_pair_body<RSP, AVG>(L.pairs, L.npairs, fl, geo, (long long)b * DSS_TPB + threadIdx.x, blockIdx.y);
+      return;
+    }
+    b -= L.nb_pair;
   }
-  b -= L.nb_pair;
-  if (b < L.nb_quad) {
-    dss_quad_body<RSP, AVG>(L.quads, L.nquads, fl, geo, (long long)b * DSS_TPB + threadIdx.x, blockIdx.y);
-    return;
+  if constexpr (PARTS & 2) {
+    if (b < L.nb_quad) {
+      dss_quad_body<RSP, AVG>(L.quads, L.nquads, fl, geo, (long long)b * DSS_TPB + threadIdx.x, blockIdx.y);
+      return;
+    }
+    b -= L.nb_quad;
   }
-  b -= L.nb_quad;
-  dss_nodes_body<RSP, AVG>(L.nodes, L.nnodes, fl, geo, L.halo, (long long)b * DSS_TPB + threadIdx.x, blockIdx.y);
+  if constexpr (PARTS & 4)
+    dss_nodes_body<RSP, AVG>(L.nodes, L.nnodes, fl, geo, L.halo, (long long)b * DSS_TPB + threadIdx.x, blockIdx.y);
 }
 
 __global__ void scale_interior_kernel(FieldList fl, const double* __restrict__ geo, int nelem) {
@@ -827,25 +861,31 @@ void dss_exchange(const FieldList& fl, bool rspheremp) {
   }
   const int ny = (fl.nf + DSS_FPB - 1) / DSS_FPB;
   const bool avg = fl.navg > 0;
-  auto nblk = [](int n) { return (int)(((long long)n * NLEV + DSS_TPB - 1) / DSS_TPB); };
-  auto launch = [&](const DssLists& L, int nb) {
-    if (!nb) return;
-    const dim3 grid(nb, ny);
-    PROBE(K_DSS);
-    if (avg && rspheremp) dss_kernel<true, true><<<grid, DSS_TPB, 0, S.stream>>>(L, fl, S.geo);
-    else if (avg) dss_kernel<false, true><<<grid, DSS_TPB, 0, S.stream>>>(L, fl, S.geo);
-    else if (rspheremp) dss_kernel<true, false><<<grid, DSS_TPB, 0, S.stream>>>(L, fl, S.geo);
-    else dss_kernel<false, false><<<grid, DSS_TPB, 0, S.stream>>>(L, fl, S.geo);
-    KERNEL_LAUNCHED(K_DSS);
-  };
+  auto nblk = [](int n) { return (int)(((long long)n * DSS_NLV + DSS_TPB - 1) / DSS_TPB); };
   DssLists L{(const DssPair*)S.dss_pairs, S.npairs, nblk(S.npairs), (const DssQuad*)S.dss_quads, S.nquads, nblk(S.nquads),
-             S.nodes, halo ? 0 : S.nnodes, recv};
-  launch(L, L.nb_pair + L.nb_quad + nblk(L.nnodes));
-  if (halo) {
+             S.nodes, S.nnodes, recv};
+#define HXX_DSS_LAUNCH(PARTS, NB)                                                                        \
+  do {                                                                                                   \
+    const int nb_ = (NB);                                                                                \
+    if (nb_) {                                                                                           \
+      const dim3 grid(nb_, ny);                                                                          \
+      PROBE(K_DSS);                                                                                      \
+      if (avg && rspheremp) dss_kernel<PARTS, true, true><<<grid, DSS_TPB, 0, S.stream>>>(L, fl, S.geo); \
+      else if (avg) dss_kernel<PARTS, false, true><<<grid, DSS_TPB, 0, S.stream>>>(L, fl, S.geo);        \
+      else if (rspheremp) dss_kernel<PARTS, true, false><<<grid, DSS_TPB, 0, S.stream>>>(L, fl, S.geo);  \
+      else dss_kernel<PARTS, false, false><<<grid, DSS_TPB, 0, S.stream>>>(L, fl, S.geo);                \
+      KERNEL_LAUNCHED(K_DSS);                                                                            \
+    }                                                                                                    \
+  } while (0)
+  HXX_DSS_LAUNCH(1, L.nb_pair);
+  if (!halo) {
+    HXX_DSS_LAUNCH(6, L.nb_quad + nblk(L.nnodes));
+  } else {
+    HXX_DSS_LAUNCH(2, L.nb_quad);
     halo_arrived();
-    DssLists G{nullptr, 0, 0, nullptr, 0, 0, S.nodes, S.nnodes, recv};
-    launch(G, nblk(S.nnodes));
+    HXX_DSS_LAUNCH(4, nblk(L.nnodes));
   }
+#undef HXX_DSS_LAUNCH
 }
 
 // Asynchronous NCCL errors (a peer that died) surface here instead of as a hang; polled once per

@@ -389,6 +389,13 @@ void finalize_hommexx_session(void) {
 
 void init_connectivity(const int* num_local_elems) {
   need_session("init_connectivity");
+  // A session that already holds a mesh is being re-initialised (a second driver bound to this library): the
+  // first mesh's arrays — including the lazily allocated forcing arrays, sized for it — go first.
+  if (S.geo || S.v || S.nbr8) {
+    CUDA_OK(cudaStreamSynchronize(S.stream));
+    CUDA_OK(cudaStreamSynchronize(S.comm_stream));
+    free_all();
+  }
   // Connectivity.cpp:40-75
   S.nelemd = *num_local_elems;
   S.conn.assign((size_t)S.nelemd * 8, ConnInfo{});

@@ -81,29 +81,81 @@ Gll make_gll() {
   return g;
 }
 
-// ---- generalized Hilbert curve over an n x n face ("gilbert") -----------------------------
-// HOMME builds its curve from Hilbert/Peano/Cinco refinements (spacecurve_mod.F90:39-899); any
-// continuous curve gives the same kind of contiguous patches, and results do not depend on the
-// partition (DSS sums are ordered per element), so a generalized Hilbert curve is used here.
-void gilbert(int x, int y, int ax, int ay, int bx, int by, std::vector<std::pair<int, int>>& out) {
-  auto sgn = [](int v) { return (v > 0) - (v < 0); };
-  int w = std::abs(ax + ay), h = std::abs(bx + by);
-  int dax = sgn(ax), day = sgn(ay), dbx = sgn(bx), dby = sgn(by);
-  if (h == 1) { for (int i = 0; i < w; ++i) { out.emplace_back(x, y); x += dax; y += day; } return; }
-  if (w == 1) { for (int i = 0; i < h; ++i) { out.emplace_back(x, y); x += dbx; y += dby; } return; }
-  int ax2 = ax / 2, ay2 = ay / 2, bx2 = bx / 2, by2 = by / 2;
-  int w2 = std::abs(ax2 + ay2), h2 = std::abs(bx2 + by2);
-  if (2 * w > 3 * h) {
-    if ((w2 % 2) && (w > 2)) { ax2 += dax; ay2 += day; }
-    gilbert(x, y, ax2, ay2, bx, by, out);
-    gilbert(x + ax2, y + ay2, ax - ax2, ay - ay2, bx, by, out);
-  } else {
-    if ((h2 % 2) && (h > 2)) { bx2 += dbx; by2 += dby; }
-    gilbert(x, y, bx2, by2, ax2, ay2, out);
-    gilbert(x + bx2, y + by2, ax, ay, bx - bx2, by - by2, out);
-    gilbert(x + (ax - dax) + (bx2 - dbx), y + (ay - day) + (by2 - dby), -bx2, -by2, -(ax - ax2),
-            -(ay - ay2), out);
+// ---- HOMME's space-filling curve over an n x n face ------------------------------------------
+// spacecurve_mod.F90:39-1040. n = 2^a 3^b 5^c is traversed by nested Hilbert (2 x 2), meandering Peano (3 x 3)
+// and Cinco (5 x 5) refinements, the factors of 2 finest and the factors of 5 coarsest (Factor :901-974,
+// map :994-1009). Each refinement visits its sub-cells in a fixed order; a sub-cell is itself a curve
+// described by a major axis / direction and a "joiner" (the unit step that leaves it). The reference spells
+// the 4 + 9 + 25 sub-cells out as code; here they are rows of one table relative to the parent's frame:
+//   {A, D, JA, JD}: major axis = (ma + A) mod 2, major direction = D * md,
+//                   joiner = JA == 2 ? the parent's own joiner : axis (ma + JA) mod 2, direction JD * md.
+struct SubCell { signed char A, D, JA, JD; };
+const SubCell HILBERT[4] = {{1, 1, 1, 1}, {0, 1, 0, 1}, {0, 1, 1, -1}, {1, -1, 2, 0}};
+const SubCell PEANO[9] = {{1, 1, 1, 1}, {1, 1, 1, 1}, {0, 1, 0, 1}, {0, 1, 0, 1}, {0, 1, 1, -1},
+                          {0, -1, 0, -1}, {1, -1, 1, -1}, {1, -1, 0, 1}, {0, 1, 2, 0}};
+const SubCell CINCO[25] = {{0, 1, 0, 1}, {0, 1, 0, 1}, {1, 1, 1, 1}, {1, 1, 1, 1}, {1, 1, 0, -1},
+                           {1, -1, 1, -1}, {0, -1, 0, -1}, {0, -1, 1, 1}, {1, 1, 1, 1}, {1, 1, 1, 1},
+                           {0, 1, 0, 1}, {0, 1, 1, -1}, {1, -1, 0, 1}, {1, 1, 1, 1}, {0, 1, 0, 1},
+                           {0, 1, 0, 1}, {0, 1, 1, -1}, {0, -1, 0, -1}, {1, -1, 1, -1}, {1, -1, 0, 1},
+                           {0, 1, 1, -1}, {0, -1, 0, -1}, {1, -1, 1, -1}, {1, -1, 0, 1}, {0, 1, 2, 0}};
+
+struct FaceCurve {
+  int n = 0;
+  std::vector<int> factors;   // finest first
+  std::vector<int> order;     // order[i + n * j] = visit number of cell (i, j) ("Mesh(i+1, j+1)")
+  int pos[2] = {0, 0}, count = 0;
+  void gen(int level, int ma, int md, int ja, int jd) {   // GenCurve :885-899
+    const int type = factors[level - 1];
+    const SubCell* t = type == 2 ? HILBERT : type == 3 ? PEANO : CINCO;
+    for (int c = 0; c < type * type; ++c) {
+      const int lma = (ma + t[c].A) & 1, lmd = t[c].D * md;
+      const int lja = t[c].JA == 2 ? ja : (ma + t[c].JA) & 1, ljd = t[c].JA == 2 ? jd : t[c].JD * md;
+      if (level > 1) gen(level - 1, lma, lmd, lja, ljd);
+      else {  // IncrementCurve :771-783
+        order[pos[0] + n * pos[1]] = count++;
+        pos[lja] += ljd;
+      }
+    }
   }
+};
+bool factor_235(int n, std::vector<int>& f) {
+  f.clear();
+  for (int p : {2, 3, 5})
+    while (n % p == 0) { f.push_back(p); n /= p; }
+  return n == 1 && !f.empty();
+}
+// Mesh(ne, ne) of CubeTopology (cube_mod.F90:1457-1523): the curve itself when ne factors into 2, 3, 5, else the
+// curve of the next power of two sampled at the ne x ne cell centres.
+std::vector<int> face_curve(int ne) {
+  FaceCurve c;
+  if (ne == 1) return {0};
+  if (factor_235(ne, c.factors)) {
+    c.n = ne;
+    c.order.assign((size_t)ne * ne, 0);
+    c.gen((int)c.factors.size(), 0, 1, 0, 1);
+    return c.order;
+  }
+  int ne2 = 1;
+  while (ne2 < ne) ne2 *= 2;
+  factor_235(ne2, c.factors);
+  c.n = ne2;
+  c.order.assign((size_t)ne2 * ne2, 0);
+  c.gen((int)c.factors.size(), 0, 1, 0, 1);
+  std::vector<int> to_small((size_t)ne2 * ne2, -1);   // Mesh2_map
+  for (int j = 1; j <= ne; ++j)
+    for (int i = 1; i <= ne; ++i) {
+      int i2 = (int)std::lround(((i - 0.5) / ne) * ne2 + 0.5), j2 = (int)std::lround(((j - 0.5) / ne) * ne2 + 0.5);
+      i2 = std::min(std::max(i2, 1), ne2);
+      j2 = std::min(std::max(j2, 1), ne2);
+      to_small[(i2 - 1) + (size_t)ne2 * (j2 - 1)] = (i - 1) + ne * (j - 1);
+    }
+  std::vector<int> where((size_t)ne2 * ne2);          // sfcij: visit number -> cell of the big mesh
+  for (int k = 0; k < ne2 * ne2; ++k) where[c.order[k]] = k;
+  std::vector<int> mesh((size_t)ne * ne, 0);
+  int idx = 0;
+  for (int k = 0; k < ne2 * ne2; ++k)
+    if (to_small[where[k]] >= 0) mesh[to_small[where[k]]] = idx++;
+  return mesh;
 }
 
 struct Vec3i {
@@ -309,13 +361,29 @@ void build_topology(HommeDriver& h) {
       }
     }
   }
-  // space-filling curve: faces chained in HOMME's order 1,2,6,4,5,3 (cube_mod.F90:1527-1587)
-  std::vector<std::pair<int, int>> curve;
-  gilbert(0, 0, ne, 0, 0, ne, curve);
-  static const int face_order[6] = {1, 2, 6, 4, 5, 3};
-  h.sfc_order.clear();
-  for (int fo = 0; fo < 6; ++fo)
-    for (auto& ij : curve) h.sfc_order.push_back(ij.first + ne * ij.second + ne * ne * (face_order[fo] - 1));
+  // The face curve laid on the six faces so that it runs on continuously from one face to the next:
+  // faces in the order 1, 2, 6, 4, 5, 3, each with its own reflection / rotation (cube_mod.F90:1527-1587).
+  // (i, j) = 1-based element indices of GridElem(i, j, face); gid = (face-1) ne^2 + (j-1) ne + (i-1).
+  {
+    const std::vector<int> mesh = face_curve(ne);
+    auto M = [&](int i, int j) { return mesh[(i - 1) + (size_t)ne * (j - 1)]; };
+    h.sfc_order.assign(h.nelem, -1);
+    static const int face_order[6] = {1, 2, 6, 4, 5, 3};
+    for (int fo = 0; fo < 6; ++fo) {
+      const int face = face_order[fo], offset = fo * ne * ne;
+      for (int j = 1; j <= ne; ++j)
+        for (int i = 1; i <= ne; ++i) {
+          int sc;
+          switch (face) {
+            case 1: case 2: sc = M(i, ne - j + 1); break;
+            case 6: sc = M(ne - i + 1, ne - j + 1); break;
+            case 4: sc = M(ne - j + 1, i); break;
+            default: sc = M(i, j); break;   // faces 5 and 3
+          }
+          h.sfc_order[offset + sc] = (face - 1) * ne * ne + (j - 1) * ne + (i - 1);
+        }
+    }
+  }
   // genspacepart (spacecurve_mod.F90:1232-1264): contiguous runs, first nelem%npart parts get +1
   const int npart = h.p.npart;
   h.owner.assign(h.nelem, 0);
