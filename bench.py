@@ -156,19 +156,45 @@ def step_bytes_per_elem_step(cfg):
     return (caar + hvt + euler + remap + updq + misc) * F_BYTES
 
 
+def native_oracle():
+    """The timing build of the CPU port: oracle.c compiled ON THIS HOST with -O3 -march=native (BASELINE.md
+    section 3; `make -C oracle native` -> oracle/_native/, git-ignored). The parity tests keep using the strict
+    liboracle.so; this one is only ever timed. Falls back to the strict build if the compile fails."""
+    from oracle import oraclelib
+    out = ROOT / "oracle" / "_native" / "liboracle_native.so"
+    try:
+        subprocess.run(["make", "-s", "-C", str(ROOT / "oracle"), "native"], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, timeout=300)
+        if out.exists():
+            return out, "gcc -O3 -march=native -ffp-contract=fast -fopenmp (built on this host)"
+    except (OSError, subprocess.SubprocessError):
+        pass
+    return oraclelib.ORACLE_LIB, "gcc -O3 -mavx2 -ffp-contract=off -fopenmp (strict parity build)"
+
+
+def cpu_sample_mesh(args, cores):
+    """The CPU arm runs the GPU arm's own configuration (ne30, 5400 elements) when the host has the cores to
+    finish in minutes, else a smaller mesh of the same namelist (element-steps/s is per-element throughput)."""
+    if args.ref_ne:
+        return args.ref_ne
+    return 30 if cores >= 12 else 15
+
+
 def run_reference(args):
     """CPU arm: the oracle port of the reference's algorithm, all host threads, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from hommexx_b200 import homme
-    from oracle import oraclelib
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    ne_s = args.ref_ne
+    os.environ["OMP_NUM_THREADS"] = str(cores)   # torchrun exports OMP_NUM_THREADS=1 to its workers
+    os.environ.setdefault("OMP_PROC_BIND", "false")
+    from hommexx_b200 import homme
+    lib, flags = native_oracle()
+    cfg = workload(args, 1)
+    ne_s = cpu_sample_mesh(args, cores)
     cfg = workload(args, 1)
     scfg = homme.preset("ne30", ne=ne_s, qsize=cfg.qsize)
-    h = homme.Homme(scfg, oraclelib.ORACLE_LIB)
+    h = homme.Homme(scfg, lib)
     h.init_dycore()
     dyn = scfg.rsplit * scfg.qsplit
     for _ in range(args.warmup):

@@ -153,6 +153,8 @@ struct Session {
   int nnodes = 0;
   void *dss_pairs = nullptr, *dss_quads = nullptr;  // lean lists (dss.cu: DssPair / DssQuad)
   int npairs = 0, nquads = 0;
+  void* dss_uni = nullptr;  // pairs and quads in one element-ordered list (dss.cu: DssQuad records)
+  int nuni = 0;
   int* nbr8 = nullptr;  // [nelemd][8] neighbour lid (>=0), ~halo_conn (<0) or DSS_NONE
   int* elem_order = nullptr;  // local elements, those without an off-rank neighbour first
   int n_interior = 0;
