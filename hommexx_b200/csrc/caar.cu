@@ -372,11 +372,15 @@ void caar_run(int nm1, int n0, int np1, double dt, double eta_ave_w, int n0_qdp,
     CUDA_OK(cudaFuncSetAttribute(caar_kernel<CAAR_E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_vadv));
   }
   const int nb = (S.nelemd + CAAR_E - 1) / CAAR_E;
+  HXX_TIMER("caar compute");
   PROBE(K_CAAR);
   if (S.p.rsplit == 0) caar_kernel<CAAR_E, true><<<nb, CAAR_E * NLEV, smem_vadv, S.stream>>>(a);
   else caar_kernel<CAAR_E, false><<<nb, CAAR_E * NLEV, smem, S.stream>>>(a);
   KERNEL_LAUNCHED(K_CAAR);
-  if (with_dss) dss_exchange(fields_caar(np1), true);  // CaarFunctor.cpp:113
+  if (with_dss) {
+    HXX_TIMER("caar_bexchV");
+    dss_exchange(fields_caar(np1), true);  // CaarFunctor.cpp:113
+  }
 }
 
 // ---- element-wise kernels -----------------------------------------------------------------

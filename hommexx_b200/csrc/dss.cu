@@ -275,12 +275,14 @@ __device__ __forceinline__ void dss_quad_apply(const DssQuad qd, const FieldList
 
 // PARTS selects what a launch covers: 1 = the pair list, 2 = the quad list, 4 = the generic nodes; the lists
 // present are consecutive block ranges (the split is block-uniform, so nothing diverges). Pairs are a launch of
-// their own — their body needs far fewer registers, and a pass this latency-bound lives on resident warps; the
-// few generic nodes of a single-rank run ride with the quads, on several ranks they wait for the halo.
+// their own — their body needs far fewer registers; the few generic nodes of a single-rank run ride with the
+// quads, on several ranks they wait for the halo. Measured at ne30 / 41 fields (profiles/r2_dss_experiments.txt):
+// the pass moves its 0.75 R + 0.75 W of every field at 4.2 TB/s whatever the unroll (2 / 4 fields in flight),
+// the fields per thread (4 / 8 / 16), the vector width, or the list order (pairs and quads interleaved in element
+// order was 5 % slower): 576-byte columns scattered over gigabytes are what bounds it, not this kernel's shape.
 struct DssLists {
   const DssPair* pairs; int npairs, nb_pair;
   const DssQuad* quads; int nquads, nb_quad;
-  const DssQuad* uni; int nuni, nb_uni;  // PARTS & 8: pairs and quads interleaved in element order
   const DssNode* nodes; int nnodes;
   const double* halo;
 };
@@ -288,18 +290,6 @@ template <int PARTS, bool RSP, bool AVG>
 __global__ void __launch_bounds__(DSS_TPB, PARTS == 1 ? (AVG ? 4 : 8) : (AVG ? 4 : HXX_DSS_MINB)) dss_kernel(DssLists L, FieldList fl,
                                                                                     const double* __restrict__ geo) {
   int b = blockIdx.x;
-  if constexpr (PARTS & 8) {
-    if (b < L.nb_uni) {
-      const long long g = (long long)b * DSS_TPB + threadIdx.x;
-      const int iu = (int)(g / DSS_NLV), k = (int)(g % DSS_NLV) * DSS_V;
-      if (iu >= L.nuni) return;
-      const DssQuad qd = L.uni[iu];
-      if (qd.m[2] < 0) dss_pair_apply<RSP, AVG>(DssPair{qd.m[0], qd.m[1]}, fl, geo, k, blockIdx.y);
-      else dss_quad_apply<RSP, AVG>(qd, fl, geo, k, blockIdx.y);
-      return;
-    }
-    b -= L.nb_uni;
-  }
   if constexpr (PARTS & 1) {
     if (b < L.nb_pair) {
       dss_pair_body<RSP, AVG>(L.pairs, L.npairs, fl, geo, (long long)b * DSS_TPB + threadIdx.x, blockIdx.y);
@@ -435,8 +425,7 @@ void free_exchange_plan() {
   if (S.nodes) { cudaFree(S.nodes); S.nodes = nullptr; }
   if (S.dss_pairs) { cudaFree(S.dss_pairs); S.dss_pairs = nullptr; }
   if (S.dss_quads) { cudaFree(S.dss_quads); S.dss_quads = nullptr; }
-  if (S.dss_uni) { cudaFree(S.dss_uni); S.dss_uni = nullptr; }
-  S.nuni = 0;
+
   S.npairs = S.nquads = 0;
   if (S.nbr8) { cudaFree(S.nbr8); S.nbr8 = nullptr; }
   if (S.elem_order) { cudaFree(S.elem_order); S.elem_order = nullptr; }
@@ -732,16 +721,13 @@ void build_exchange_plan() {
   }
   // -- split into the lean pair / quad lists and the generic remainder
   std::vector<DssPair> pairs;
-  std::vector<DssQuad> quads, uni;  // uni = pairs and quads in node (= element) order, a pair has m[2] < 0
+  std::vector<DssQuad> quads;
   std::vector<DssNode> rest;
   for (const DssNode& nd : nodes) {
     bool local = true;
     for (int m = 0; m < nd.nmem; ++m) local = local && nd.src[m] >= 0;
     if (local && nd.nmem == 2 && nd.ord[0][0] == 1 && nd.ord[0][1] == 255 && nd.ord[1][0] == 0 && nd.ord[1][1] == 255) {
       pairs.push_back({nd.src[0], nd.src[1]});
-      DssQuad u{};
-      u.m[0] = nd.src[0]; u.m[1] = nd.src[1]; u.m[2] = u.m[3] = -1;
-      uni.push_back(u);
       continue;
     }
     if (local && nd.nmem == 4 && nd.ord[0][2] < 4) {
@@ -769,7 +755,6 @@ void build_exchange_plan() {
         for (int i = 0; i < 4; ++i) q.m[i] = nd.src[C[i]];
         q.swaps = swaps;
         quads.push_back(q);
-        uni.push_back(q);
         continue;
       }
     }
@@ -790,11 +775,7 @@ void build_exchange_plan() {
     CUDA_OK(cudaMalloc(&S.dss_quads, quads.size() * sizeof(DssQuad)));
     CUDA_OK(cudaMemcpy(S.dss_quads, quads.data(), quads.size() * sizeof(DssQuad), cudaMemcpyHostToDevice));
   }
-  S.nuni = (int)uni.size();
-  if (S.nuni) {
-    CUDA_OK(cudaMalloc(&S.dss_uni, uni.size() * sizeof(DssQuad)));
-    CUDA_OK(cudaMemcpy(S.dss_uni, uni.data(), uni.size() * sizeof(DssQuad), cudaMemcpyHostToDevice));
-  }
+
   // -- neighbour table for the min/max exchange
   std::vector<int> nbr8((size_t)n * 8, DSS_NONE);
   for (int ie = 0; ie < n; ++ie)
@@ -904,8 +885,7 @@ void dss_exchange(const FieldList& fl, bool rspheremp) {
   const bool avg = fl.navg > 0;
   auto nblk = [](int n) { return (int)(((long long)n * DSS_NLV + DSS_TPB - 1) / DSS_TPB); };
   DssLists L{(const DssPair*)S.dss_pairs, S.npairs, nblk(S.npairs), (const DssQuad*)S.dss_quads, S.nquads, nblk(S.nquads),
-             (const DssQuad*)S.dss_uni, S.nuni, nblk(S.nuni), S.nodes, S.nnodes, recv};
-  static const bool unified = [] { const char* e = std::getenv("HXX_DSS_UNIFIED"); return e && std::atoi(e) != 0; }();
+             S.nodes, S.nnodes, recv};
 #define HXX_DSS_LAUNCH(PARTS, NB)                                                                        \
   do {                                                                                                   \
     const int nb_ = (NB);                                                                                \
@@ -919,15 +899,6 @@ void dss_exchange(const FieldList& fl, bool rspheremp) {
       KERNEL_LAUNCHED(K_DSS);                                                                            \
     }                                                                                                    \
   } while (0)
-  if (unified) {
-    if (!halo) HXX_DSS_LAUNCH(12, L.nb_uni + nblk(L.nnodes));
-    else {
-      HXX_DSS_LAUNCH(8, L.nb_uni);
-      halo_arrived();
-      HXX_DSS_LAUNCH(4, nblk(L.nnodes));
-    }
-    return;
-  }
   HXX_DSS_LAUNCH(1, L.nb_pair);
   if (!halo) {
     HXX_DSS_LAUNCH(6, L.nb_quad + nblk(L.nnodes));

@@ -291,10 +291,16 @@ void hypervis_run(int np1, double dt_in, double eta_ave_w) {
     CUDA_OK(cudaFuncSetAttribute(hv_second_vector_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb));
   }
   for (int icycle = 0; icycle < p.hypervis_subcycle; ++icycle) {
-    PROBE(K_HV_FIRST);
-    hv_first_laplace_kernel<<<nb, TPB, park_bytes, S.stream>>>(a);
-    KERNEL_LAUNCHED(K_HV_FIRST);
-    dss_exchange(fields_hv(), true);
+    {
+      HXX_TIMER("hvf-bhwk");
+      PROBE(K_HV_FIRST);
+      hv_first_laplace_kernel<<<nb, TPB, park_bytes, S.stream>>>(a);
+      KERNEL_LAUNCHED(K_HV_FIRST);
+    }
+    {
+      HXX_TIMER("hvf-bexch");
+      dss_exchange(fields_hv(), true);
+    }
     {
       const int nsp = p.nu_top > 0 ? (NLEV < 3 ? NLEV : 3) : 0;  // NUM_BIHARMONIC_LEV
       const int nb_main = (int)(((long long)S.nelemd * (NLEV - nsp) + TPB - 1) / TPB);
@@ -313,7 +319,10 @@ void hypervis_run(int np1, double dt_in, double eta_ave_w) {
       KERNEL_LAUNCHED(K_HV_SECOND);
       S.launches += 3;
     }
-    dss_exchange(fields_hv(), false);
+    {
+      HXX_TIMER("hvf-bexch");
+      dss_exchange(fields_hv(), false);
+    }
     PROBE(K_HV_UPDATE);
     hv_update_states_kernel<<<S.nelemd, 288, 0, S.stream>>>(a);
     KERNEL_LAUNCHED(K_HV_UPDATE);

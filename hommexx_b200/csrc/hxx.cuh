@@ -153,8 +153,6 @@ struct Session {
   int nnodes = 0;
   void *dss_pairs = nullptr, *dss_quads = nullptr;  // lean lists (dss.cu: DssPair / DssQuad)
   int npairs = 0, nquads = 0;
-  void* dss_uni = nullptr;  // pairs and quads in one element-ordered list (dss.cu: DssQuad records)
-  int nuni = 0;
   int* nbr8 = nullptr;  // [nelemd][8] neighbour lid (>=0), ~halo_conn (<0) or DSS_NONE
   int* elem_order = nullptr;  // local elements, those without an off-rank neighbour first
   int n_interior = 0;
@@ -216,6 +214,20 @@ void probe_end(int id);
     seen = ::hxx::S.session_id;                          \
     return true;                                         \
   }())
+
+// NVTX ranges named after the reference's GPTL timers (profiling.hpp:13-51 and the start_timer calls of
+// prim_driver.cpp, prim_step.cpp, prim_advance_exp.cpp, prim_advec_tracers_remap.cpp, CaarFunctor.cpp,
+// HyperviscosityFunctorImpl.cpp): the reference cannot time on CUDA ("Can't use GPTL timers on CUDA"); here the
+// same names show up on the host timeline of nsys / ncu --nvtx. Header-only; a no-op without a profiler attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name);
+  ~NvtxRange();
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define HXX_TIMER_CAT2(a, b) a##b
+#define HXX_TIMER_CAT(a, b) HXX_TIMER_CAT2(a, b)
+#define HXX_TIMER(name) ::hxx::NvtxRange HXX_TIMER_CAT(hxx_timer_, __LINE__) { name }
 
 // per-translation-unit constant bank (no relocatable device code: each TU owns a copy)
 void register_const_uploader(void (*fn)(const DevConst&));

@@ -8,6 +8,7 @@
 #include <string>
 
 #include "hxx.cuh"
+#include <nvtx3/nvToolsExt.h>
 #ifdef HXX_WITH_NCCL
 #include <nccl.h>
 #endif
@@ -15,6 +16,9 @@
 namespace hxx {
 
 Session S;
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 static std::vector<void (*)(const DevConst&)>& uploaders() {
   static std::vector<void (*)(const DevConst&)> u;
@@ -180,6 +184,7 @@ static void update_dynamics_levels() {  // LEAPFROG :37-56
 
 // prim_advance_exp.cpp:113-161
 static void u3_5stage_timestep(int nm1, int n0, int np1, int n0_qdp, double dt, double eta_ave_w) {
+  HXX_TIMER("tl-ae U3-5stage_timestep");
   caar_run(n0, n0, nm1, dt / 5.0, eta_ave_w / 4.0, n0_qdp, true);
   caar_run(n0, nm1, np1, dt / 5.0, 0.0, n0_qdp, true);
   caar_run(n0, np1, np1, dt / 3.0, 0.0, n0_qdp, true);
@@ -190,28 +195,50 @@ static void u3_5stage_timestep(int nm1, int n0, int np1, int n0_qdp, double dt, 
 
 // prim_advec_tracers_remap.cpp:32-90
 static void prim_advec_tracers_remap_RK2(double dt) {
+  HXX_TIMER("tl-at prim_advec_tracers_remap_RK2");
   update_tracers_levels();
   S.rhs_viss = 0.0;  // EulerStepFunctor::reset
-  euler_precompute_divdp();
-  euler_step(S.np1_qdp, S.n0_qdp, dt / 2.0, 0.0, DSS_DIV_VDP_AVE);
-  euler_step(S.np1_qdp, S.np1_qdp, dt / 2.0, 1.0, DSS_ETA);
-  // the last stage also applies qdp_time_avg(n0_qdp, np1_qdp) (:88), fused into its stores
-  euler_step(S.np1_qdp, S.np1_qdp, dt / 2.0, 2.0, DSS_OMEGA, S.n0_qdp);
+  {
+    HXX_TIMER("tl-at precompute_divdp");
+    euler_precompute_divdp();
+  }
+  {
+    HXX_TIMER("tl-at esf-0");
+    euler_step(S.np1_qdp, S.n0_qdp, dt / 2.0, 0.0, DSS_DIV_VDP_AVE);
+  }
+  {
+    HXX_TIMER("tl-at esf-1");
+    euler_step(S.np1_qdp, S.np1_qdp, dt / 2.0, 1.0, DSS_ETA);
+  }
+  {
+    // the last stage also applies qdp_time_avg(n0_qdp, np1_qdp) (:88, "tl-at qdp_time_avg"), fused into its stores
+    HXX_TIMER("tl-at esf-2");
+    euler_step(S.np1_qdp, S.np1_qdp, dt / 2.0, 2.0, DSS_OMEGA, S.n0_qdp);
+  }
 }
 
 // prim_step.cpp:20-103
 static void prim_step(double dt) {
-  prim_step_init(S.n0);
+  HXX_TIMER("tl-s prim_step");
+  {
+    HXX_TIMER("tl-s deep_copy+derived_dp");
+    prim_step_init(S.n0);
+  }
   for (int nq = 0; nq < S.p.qsplit; ++nq) {
+    HXX_TIMER("tl-ae prim_advance_exp");
     if (nq > 0) update_dynamics_levels();
     // prim_advance_exp.cpp:25-111
     S.n0_qdp = -1;
     if (S.p.moist) update_tracers_levels();
     const double eta_ave_w = 1.0 / S.p.qsplit;
     u3_5stage_timestep(S.nm1, S.n0, S.np1, S.n0_qdp, dt, eta_ave_w);
+    HXX_TIMER("tl-ae advance_hypervis_dp");
     hypervis_run(S.np1, dt, eta_ave_w);
   }
-  if (S.p.qsize > 0) prim_advec_tracers_remap_RK2(dt * S.p.qsplit);
+  if (S.p.qsize > 0) {
+    HXX_TIMER("tl-s prim_advec_tracers_remap");
+    prim_advec_tracers_remap_RK2(dt * S.p.qsplit);
+  }
 }
 
 struct NamedField { const char* nm; double* p; size_t n; };
@@ -583,6 +610,7 @@ void init_time_level_c(const int* nm1, const int* n0, const int* np1, const int*
 // prim_driver.cpp:31-156
 void prim_run_subcycle_c(const double* dt, int* nstep, int* nm1, int* n0, int* np1, const int* last_time_step) {
   need_session("prim_run_subcycle_c");
+  HXX_TIMER("tl-sc prim_run_subcycle_c");
   if (!S.p.params_set) runtime_abort("prim_run_subcycle_c: simulation params not set", 13);
   if (!S.nodes && S.nelemd > 0 && !S.nbr8) runtime_abort("prim_run_subcycle_c: init_boundary_exchanges_c not called", 13);
   const double dt_q = *dt * S.p.qsplit;
@@ -603,19 +631,31 @@ void prim_run_subcycle_c(const double* dt, int* nstep, int* nm1, int* n0, int* n
   }
   update_tracers_levels();
   // :76-82 — every standalone namelist has ftype = 0: the pass runs with zero forcing arrays
-  if (S.p.ftype == 0) apply_cam_forcing(dt_remap, true);
-  else if (S.p.ftype == 2) apply_cam_forcing(dt_remap, false);
+  if (S.p.ftype == 0) {
+    HXX_TIMER("ApplyCAMForcing");
+    apply_cam_forcing(dt_remap, true);
+  } else if (S.p.ftype == 2) {
+    HXX_TIMER("ApplyCAMForcing_dynamics");
+    apply_cam_forcing(dt_remap, false);
+  }
   if (compute_diagnostics) {
     prim_energy_halftimes(true, 0);
     prim_diag_scalars(true, 0);
   }
-  dp3d_from_ps(S.n0);  // :98-111
-  prim_step(*dt);
-  for (int r = 1; r < S.p.rsplit; ++r) {
-    update_dynamics_levels();
+  {
+    HXX_TIMER("tl-sc dp3d-from-ps");
+    dp3d_from_ps(S.n0);  // :98-111
+  }
+  {
+    HXX_TIMER("tl-sc prim_step-loop");
     prim_step(*dt);
+    for (int r = 1; r < S.p.rsplit; ++r) {
+      update_dynamics_levels();
+      prim_step(*dt);
+    }
   }
   update_tracers_levels();
+  HXX_TIMER("tl-sc vertical_remap");
   // :131 and :138 — the remap kernel also stores Q = Qdp / dp for every tracer (update_q fused
   // into its tracer store); without tracers there is nothing to update
   vertical_remap(S.np1, S.np1_qdp, dt_remap);
