@@ -249,7 +249,11 @@ def main():
     ap.add_argument("--qsize", type=int, default=0)
     ap.add_argument("--ref-ne", type=int, default=0, help="mesh of the bounded CPU sample (default: ne30 itself)")
     ap.add_argument("--weak", action="store_true", help="N>1: weak-scaling meshes instead of ne120 strong scaling")
-    ap.add_argument("--no-fma", action="store_true", help="skip the timing of the FMA-contracted build")
+    ap.add_argument("--flavour", default="fma", choices=["fma", "strict"],
+                    help="build that is benchmarked: fma = multiply-adds contracted (parity <= 1e-11, the default), "
+                         "strict = --fmad=false (bit-identical to the oracle)")
+    ap.add_argument("--no-other-build", "--no-fma", dest="no_other", action="store_true",
+                    help="skip the timing of the other build beside the benchmarked one")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -281,7 +285,10 @@ def main():
 
     cfg = workload(args, n_gpus)
     cfg.part_id = rank
-    libpath = homme.cuda_lib_path(cfg.nlev, cfg.qsize_d)
+    flavour = "" if args.flavour == "strict" else "fma"
+    if flavour and not homme.cuda_lib_path(cfg.nlev, cfg.qsize_d, flavour).exists():
+        flavour = ""   # only the flagship (nlev, qsize_d) has an FMA build
+    libpath = homme.cuda_lib_path(cfg.nlev, cfg.qsize_d, flavour)
     lib = homme.load_dycore(libpath)
     lib.hommexx_b200_event_elapsed_ms.restype = C.c_double
     lib.hommexx_b200_profile.argtypes = [C.c_ulonglong]
@@ -444,14 +451,19 @@ def main():
         while PINNED:
             rt.cudaHostUnregister(PINNED.pop())
 
-    # ---- the FMA-contracted build of the same sources (parity <= 1e-11, tests/test_cuda_q40.py) ----
-    fma = None
-    fma_path = homme.cuda_lib_path(cfg.nlev, cfg.qsize_d, "fma")
-    if not args.no_fma and n_gpus == 1 and fma_path.exists():
+    # ---- the other build of the same sources, timed beside the benchmarked one (N = 1) --------------
+    BUILD_NOTE = {"fma": "--fmad=true: multiply-adds contracted; matches the oracle to <= 1e-11 (measured ~1e-14) on v, T, "
+                         "dp3d, ps, Qdp, Q after 10 steps (tests/test_cuda_q40.py::test_fma_build_*)",
+                  "": "--fmad=false: no contraction; bit-identical to the oracle per phase and after 10-12 steps "
+                      "(tests/test_cuda_q40.py, tests/test_cuda_timestep.py)"}
+    other = None
+    other_flav = "" if flavour else "fma"
+    other_path = homme.cuda_lib_path(cfg.nlev, cfg.qsize_d, other_flav)
+    if not args.no_other and n_gpus == 1 and other_path.exists() and other_path != libpath:
         unpin_all()
         h.close()
         h = None
-        hf = homme.Homme(cfg, fma_path)
+        hf = homme.Homme(cfg, other_path)
         lf = hf.lib
         lf.hommexx_b200_event_elapsed_ms.restype = C.c_double
         lf.hommexx_b200_set_comm(0, 1, local_rank, None)
@@ -465,10 +477,8 @@ def main():
         lf.hommexx_b200_event_record(1)
         lf.hommexx_b200_sync()
         fms = lf.hommexx_b200_event_elapsed_ms(0, 1)
-        fma = {"value": hf.nelem * dyn * args.steps / (fms * 1e-3), "unit": "element-steps/s",
-               "ms_per_step": fms / args.steps, "library": fma_path.name,
-               "what": "same sources compiled with --fmad=true (multiply-adds contracted); matches the oracle to "
-                       "<= 1e-11 on v, T, dp3d, ps, Qdp, Q after 10 steps instead of bit for bit"}
+        other = {"value": hf.nelem * dyn * args.steps / (fms * 1e-3), "unit": "element-steps/s",
+                 "ms_per_step": fms / args.steps, "library": other_path.name, "what": BUILD_NOTE[other_flav]}
         hf.close()
 
     # ---- CPU baseline beside it (rank 0, N = 1) -------------------------------------------------
@@ -507,7 +517,8 @@ def main():
                "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
                "step_roofline": {"algorithmic_bytes_per_element_step": step_bytes, "achieved_gbs_per_gpu": step_gbs,
                                  "frac": step_gbs / peak, "peak": peak},
-               "e2e": e2e, "e2e_coupled": e2e_coupled, "fma_build": fma, "cpu_baseline": cpu, "breakdown": breakdown}
+               "e2e": e2e, "e2e_coupled": e2e_coupled, "build": {"library": libpath.name, "what": BUILD_NOTE[flavour]},
+               ("strict_build" if flavour else "fma_build"): other, "cpu_baseline": cpu, "breakdown": breakdown}
         emit(out)
     if h is not None:
         unpin_all()

@@ -71,14 +71,14 @@ __global__ void __launch_bounds__(256) tracer_forcing_kernel(double* __restrict_
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const double r = qs[j] + clamped_increment(qs[j], dt * fv[j]);
-      qd[(size_t)(q + j) * NLF] = r;
+      if (f) qd[(size_t)(q + j) * NLF] = r;  // no forcing ever pushed: qdp + 0 is qdp, nothing to write back
       out[(size_t)(q + j) * NLF] = div_rcp(r, dp, rdp);
     }
   }
   for (; q < qsize; ++q) {
     const double qs = qd[(size_t)q * NLF];
     const double r = qs + clamped_increment(qs, dt * (f ? f[(size_t)q * NLF] : 0.0));
-    qd[(size_t)q * NLF] = r;
+    if (f) qd[(size_t)q * NLF] = r;
     out[(size_t)q * NLF] = div_rcp(r, dp, rdp);
   }
 }
@@ -112,6 +112,57 @@ void apply_cam_forcing(double dt, bool tracers) {
                                                                              S.p.qsize, S.n0, S.n0_qdp, dt);
     KERNEL_LAUNCHED(K_FORCING);
   }
+}
+
+// ---- Held-Suarez forcing on the device -------------------------------------------------------------
+// hs_T_forcing (held_suarez_mod.F90:175-279, scalar branch) and hs_v_forcing (:123-173) at time level n0, one thread
+// per (element, point, level); FM, FT are overwritten (the Fortran driver zeroes them before hs_forcing adds).
+__global__ void __launch_bounds__(256) held_suarez_kernel(const double* __restrict__ v, const double* __restrict__ t,
+                                                          const double* __restrict__ ps_v, const double* __restrict__ lat,
+                                                          const double* __restrict__ hy, double* __restrict__ fm,
+                                                          double* __restrict__ ft, int nelem, int n0) {
+  const long long gidx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (gidx >= (long long)nelem * NLF) return;
+  const int ie = (int)(gidx / NLF), i = (int)(gidx % NLF);
+  const int p = i / NLEV, k = i % NLEV;
+  constexpr double sigma_b = 0.70, secpday = 86400.0;
+  constexpr double k_a = 1.0 / (40.0 * secpday), k_f = 1.0 / (1.0 * secpday), k_s = 1.0 / (4.0 * secpday);
+  constexpr double dT_y = 60.0, dtheta_z = 10.0;
+  const double hyam = hy[k], hybm = hy[NLEV + k];
+  const double ps = ps_v[((size_t)ie * NTL + n0) * NPSQ + p];
+  const double snlat = sin(lat[(size_t)ie * NPSQ + p]);
+  const double snlatsq = snlat * snlat, cslatsq = 1.0 - snlatsq;
+  const double pm = hyam * dc.ps0 + hybm * ps;
+  const double logprat = log(pm) - log(dc.ps0);
+  const double pratk = exp(kappa * logprat);
+  const double etam = hyam + hybm;
+  const double ramp = fmax(0.0, (etam - sigma_b) / (1.0 - sigma_b));
+  const double k_t = k_a + (k_s - k_a) * cslatsq * cslatsq * ramp;
+  const double Teq = fmax(200.0, (315.0 - dT_y * snlatsq - dtheta_z * logprat * cslatsq) * pratk);
+  ft[off_f(ie) + i] = -k_t * (t[off_s(ie, n0) + i] - Teq);
+  const double k_v = k_f * ramp;
+  fm[((size_t)ie * 2 + 0) * NLF + i] = -k_v * v[off_v(ie, n0, 0) + i];
+  fm[((size_t)ie * 2 + 1) * NLF + i] = -k_v * v[off_v(ie, n0, 1) + i];
+}
+
+void held_suarez_forcing(const double* lat, const double* hyam, const double* hybm) {
+  if (!S.nelemd) return;
+  const size_t f3 = (size_t)S.nelemd * NLF;
+  if (!S.hs_lat) {
+    if (!lat || !hyam || !hybm) runtime_abort("hxx_held_suarez_forcing: the first call of a session needs lat, hyam, hybm", 13);
+    CUDA_OK(cudaMalloc(&S.hs_lat, (size_t)S.nelemd * NPSQ * sizeof(double)));
+    CUDA_OK(cudaMalloc(&S.hs_hyam, 2 * NLEV * sizeof(double)));
+    CUDA_OK(cudaMemcpyAsync(S.hs_lat, lat, (size_t)S.nelemd * NPSQ * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+    CUDA_OK(cudaMemcpyAsync(S.hs_hyam, hyam, NLEV * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+    CUDA_OK(cudaMemcpyAsync(S.hs_hyam + NLEV, hybm, NLEV * sizeof(double), cudaMemcpyHostToDevice, S.stream));
+    CUDA_OK(cudaStreamSynchronize(S.stream));
+  }
+  if (!S.fm) CUDA_OK(cudaMalloc(&S.fm, f3 * 2 * sizeof(double)));
+  if (!S.ft) CUDA_OK(cudaMalloc(&S.ft, f3 * sizeof(double)));
+  PROBE(K_FORCING);
+  held_suarez_kernel<<<(unsigned)((f3 + 255) / 256), 256, 0, S.stream>>>(S.v, S.t, S.ps_v, S.hs_lat, S.hs_hyam, S.fm, S.ft,
+                                                                      S.nelemd, S.n0);
+  KERNEL_LAUNCHED(K_FORCING);
 }
 
 // ---- diagnostics ------------------------------------------------------------------------------

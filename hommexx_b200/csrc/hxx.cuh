@@ -147,6 +147,7 @@ struct Session {
   double *vtens = nullptr, *ttens = nullptr, *dptens = nullptr;
   double *vstar = nullptr, *dpdissk = nullptr, *dp_star = nullptr;  // test-visible scratch
   double *qdp = nullptr, *qtens_biharmonic = nullptr, *qlim = nullptr, *qlim_x = nullptr, *Q = nullptr;
+  double *hs_lat = nullptr, *hs_hyam = nullptr;  // Held-Suarez inputs: [ie][16] latitudes, [2][NLEV] hyam | hybm
   double *fm = nullptr, *ft = nullptr, *fq = nullptr;  // CAM forcing [ie][2][16][NLEV], [ie][16][NLEV], [ie][QSIZE_D][16][NLEV]
   // exchange plan
   DssNode* nodes = nullptr;  // generic remainder (cube vertices, nodes with off-rank sharers)
@@ -337,6 +338,7 @@ void euler_qdp_time_avg(int n0_qdp, int np1_qdp);
 void apply_cam_forcing(double dt, bool tracers);  // CamForcing.cpp:149-174 (tracers = false: _dynamics)
 void prim_diag_scalars(bool before_advance, int ivar);
 void prim_energy_halftimes(bool before_advance, int ivar);
+void held_suarez_forcing(const double* lat, const double* hyam, const double* hybm);  // forcing_diag.cu
 void push_Q_to_host(double* host_q);  // hxx_session.cu: device Q -> F90 layout
 void* diag_scratch(size_t bytes);     // hxx_session.cu: persistent device buffer of the diagnostic sums
 // remap.cu

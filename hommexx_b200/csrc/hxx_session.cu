@@ -160,7 +160,7 @@ static void free_all() {
   dfree(S.divdp); dfree(S.divdp_proj); dfree(S.dpdiss_ave); dfree(S.dpdiss_biharmonic);
   dfree(S.vtens); dfree(S.ttens); dfree(S.dptens); dfree(S.vstar); dfree(S.dpdissk); dfree(S.dp_star);
   dfree(S.qdp); dfree(S.qtens_biharmonic); dfree(S.qlim); dfree(S.qlim_x); dfree(S.Q);
-  dfree(S.fm); dfree(S.ft); dfree(S.fq);
+  dfree(S.fm); dfree(S.ft); dfree(S.fq); dfree(S.hs_lat); dfree(S.hs_hyam);
   free_exchange_plan();
   dfree(S.invalid_flag);
   if (S.h_invalid) { cudaFreeHost(S.h_invalid); S.h_invalid = nullptr; }
@@ -737,6 +737,10 @@ void hxx_apply_forcing(double dt) {
   update_tracers_levels();
   if (S.p.ftype == 0) apply_cam_forcing(dt, true);
   else if (S.p.ftype == 2) apply_cam_forcing(dt, false);
+}
+void hxx_held_suarez_forcing(const double* lat, const double* hyam, const double* hybm) {
+  need_session("hxx_held_suarez_forcing");
+  held_suarez_forcing(lat, hyam, hybm);
 }
 void hxx_diagnostics(int before_advance, int ivar_scalars, int ivar_energy) {
   update_tracers_levels();

@@ -554,7 +554,7 @@ void jw_init(HommeDriver& h) {
   for (auto& a : h.accum) a.assign((size_t)n * 4 * std::max(1, p.qsize_d) * NPSQ, 0.0);
   h.FM.assign((size_t)n * nlev * 2 * NPSQ, 0.0);
   h.FT.assign((size_t)n * nlev * NPSQ, 0.0);
-  h.FQ.assign((size_t)n * p.qsize_d * nlev * NPSQ, 0.0);
+  h.FQ.clear();  // 40 tiles per element: allocated on first use (need_FQ), a standalone run never touches it
   for (int l = 0; l < n; ++l)
     for (int pt = 0; pt < NPSQ; ++pt) {
       const double lat = h.lat[(size_t)l * NPSQ + pt], lon = h.lon[(size_t)l * NPSQ + pt];
@@ -784,11 +784,17 @@ void hd_push_results(HommeDriver* h) {
 }
 
 // prim_driver_mod.F90:1380 / :1402 (the CAM-coupled prim_run_subcycle wrapper)
+static void need_FQ(HommeDriver* h) {
+  const size_t n = (size_t)h->nelemd * h->p.qsize_d * h->p.nlev * NPSQ;
+  if (h->FQ.size() != n) h->FQ.assign(n, 0.0);
+}
 void hd_push_forcing(HommeDriver* h) {
+  need_FQ(h);
   get_sym<void (*)(double*, double*, double*, double*)>(h, "f90_push_forcing_to_cxx")(h->FM.data(), h->FT.data(),
                                                                                      h->FQ.data(), h->Qdp.data());
 }
 void hd_pull_forcing(HommeDriver* h) {
+  need_FQ(h);
   get_sym<void (*)(double*, double*, double*)>(h, "cxx_push_forcing_to_f90")(h->FM.data(), h->FT.data(), h->FQ.data());
 }
 void hd_set_last_step(HommeDriver* h, int nEndStep) { h->last_step = nEndStep; }
@@ -809,7 +815,7 @@ double* hd_array(HommeDriver* h, const char* name, int64_t* n) {
   else if (s == "Q") a = &h->Q; else if (s == "ps_v") a = &h->ps_v; else if (s == "omega_p") a = &h->omega_p;
   else if (s == "lat") a = &h->lat; else if (s == "lon") a = &h->lon; else if (s == "gid") a = &h->gidf;
   else if (s == "tensorvisc") a = &h->tensorvisc; else if (s == "vec_sph2cart") a = &h->vec_sph2cart;
-  else if (s == "FM") a = &h->FM; else if (s == "FT") a = &h->FT; else if (s == "FQ") a = &h->FQ;
+  else if (s == "FM") a = &h->FM; else if (s == "FT") a = &h->FT; else if (s == "FQ") { need_FQ(h); a = &h->FQ; }
   else if (s == "Qvar") a = &h->accum[0]; else if (s == "Qmass") a = &h->accum[1]; else if (s == "Q1mass") a = &h->accum[2];
   else if (s == "IEner") a = &h->accum[3]; else if (s == "IEner_wet") a = &h->accum[4];
   else if (s == "KEner") a = &h->accum[5]; else if (s == "PEner") a = &h->accum[6];

@@ -183,6 +183,8 @@ def load_dycore(path) -> C.CDLL:
     lib.hxx_prim_step_init.argtypes = [C.c_int]
     lib.hxx_apply_forcing.argtypes = [C.c_double]
     lib.hxx_apply_forcing.restype = None
+    lib.hxx_held_suarez_forcing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hxx_held_suarez_forcing.restype = None
     lib.hxx_diagnostics.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.hxx_diagnostics.restype = None
     lib.hxx_exchange.argtypes = [C.c_char_p, C.c_int]
@@ -242,6 +244,11 @@ class Homme:
 
     def pull_forcing(self):
         self.d.hd_pull_forcing(self.h)
+
+    def held_suarez_forcing(self):
+        """hxx_held_suarez_forcing: FM, FT from the dycore's own state at n0, evaluated where the state lives."""
+        self.lib.hxx_held_suarez_forcing(self.array("lat").ctypes.data, self.vcoord[2].ctypes.data,
+                                         self.vcoord[3].ctypes.data)
 
     def set_last_step(self, n_end_step: int):
         self.d.hd_set_last_step(self.h, n_end_step)

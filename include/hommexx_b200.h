@@ -153,6 +153,14 @@ void hxx_prim_step_init(int n0);
 /* apply_cam_forcing (ftype 0) / apply_cam_forcing_dynamics (ftype 2), CamForcing.cpp:149-174, on
  * time level n0 / n0_qdp with the FM, FT, FQ last pushed by f90_push_forcing_to_cxx */
 void hxx_apply_forcing(double dt);
+/* Held-Suarez (1994) forcing evaluated where the state lives (hs_forcing, hs_T_forcing, hs_v_forcing of
+ * physics/heldsuarez/held_suarez_mod.F90:36-279, dry part): FM, FT of the session are OVERWRITTEN with the
+ * Newtonian relaxation of T(n0) towards T_eq(lat, p) and the Rayleigh friction on v(n0) below sigma_b = 0.7,
+ * FQ is left alone (never pushed = zero). The GPU-resident equivalent of the Fortran physics followed by
+ * f90_push_forcing_to_cxx, without the host round trip of every tracer; the next prim_run_subcycle_c applies it
+ * (ftype = 0). lat = [nelemd][np][np] latitudes, read on the first call of a session (may be null afterwards);
+ * hyam, hybm = the [nlev] mid-level coefficients init_hvcoord_c was given. */
+void hxx_held_suarez_forcing(const double* lat, const double* hyam, const double* hybm);
 /* Diagnostics::prim_diag_scalars + prim_energy_halftimes, Diagnostics.cpp:37-185, into the arrays
  * registered with init_diagnostics_c */
 void hxx_diagnostics(int before_advance, int ivar_scalars, int ivar_energy);

@@ -1699,6 +1699,39 @@ static void prim_energy_halftimes(bool before_advance, int ivar) {
     }
 }
 
+/* Held-Suarez forcing, physics/heldsuarez/held_suarez_mod.F90:123-279 (scalar branches of hs_v_forcing and
+ * hs_T_forcing) on time level n0; FM, FT overwritten. The checker of the product's device kernel. */
+void hxx_held_suarez_forcing(const double* lat, const double* hyam, const double* hybm) {
+  const int nlev = O.nlev, n0 = O.n0;
+  const double sigma_b = 0.70, secpday = 86400.0;
+  const double k_a = 1.0 / (40.0 * secpday), k_f = 1.0 / (1.0 * secpday), k_s = 1.0 / (4.0 * secpday);
+  const double dT_y = 60.0, dtheta_z = 10.0;
+  if (!O.fm) O.fm = zalloc((size_t)O.nelemd * 2 * NLF);
+  if (!O.ft) O.ft = zalloc((size_t)O.nelemd * NLF);
+  if (!O.fq) O.fq = zalloc((size_t)O.nelemd * O.qsize_d * NLF);
+  const double logps0 = log(O.ps0);
+#pragma omp parallel for
+  for (int ie = 0; ie < O.nelemd; ++ie)
+    for (int p = 0; p < NPSQ; ++p) {
+      const double ps = O.ps_v[((size_t)ie * NTL + n0) * NPSQ + p];
+      const double snlat = sin(lat[(size_t)ie * NPSQ + p]);
+      const double snlatsq = snlat * snlat, cslatsq = 1.0 - snlatsq;
+      for (int k = 0; k < nlev; ++k) {
+        const double pm = hyam[k] * O.ps0 + hybm[k] * ps;
+        const double logprat = log(pm) - logps0;
+        const double pratk = exp(kappa * logprat);
+        const double etam = hyam[k] + hybm[k];
+        const double ramp = fmax(0.0, (etam - sigma_b) / (1.0 - sigma_b));
+        const double k_t = k_a + (k_s - k_a) * cslatsq * cslatsq * ramp;
+        const double Teq = fmax(200.0, (315.0 - dT_y * snlatsq - dtheta_z * logprat * cslatsq) * pratk);
+        O.ft[F3(ie) + IX(p, k)] = -k_t * (TFLD(ie, n0)[IX(p, k)] - Teq);
+        const double k_v = k_f * ramp;
+        O.fm[((size_t)ie * 2 + 0) * NLF + IX(p, k)] = -k_v * VFLD(ie, n0, 0)[IX(p, k)];
+        O.fm[((size_t)ie * 2 + 1) * NLF + IX(p, k)] = -k_v * VFLD(ie, n0, 1)[IX(p, k)];
+      }
+    }
+}
+
 void hxx_apply_forcing(double dt) {
   update_tracers_levels();
   if (O.ftype == 0) apply_cam_forcing(dt);

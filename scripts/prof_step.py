@@ -13,9 +13,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--ne", type=int, default=30)
 ap.add_argument("--qsize", type=int, default=40)
 ap.add_argument("--steps", type=int, default=1)
+ap.add_argument("--flavour", default="", help='"" = strict build, "fma" = the FMA-contracted build')
 a = ap.parse_args()
 cfg = homme.preset("ne30", ne=a.ne, qsize=a.qsize)
-h = homme.Homme(cfg, homme.cuda_lib_path(cfg.nlev, cfg.qsize_d))
+h = homme.Homme(cfg, homme.cuda_lib_path(cfg.nlev, cfg.qsize_d, a.flavour))
 h.init_dycore()
 for _ in range(a.steps):
     h.run_subcycle()

@@ -75,3 +75,29 @@ def test_diagnostics_parity(cpstar):
         assert np.array_equal(a[k], b[k]), k
     assert np.abs(b["IEner"]).max() > 0
     hc.close(); ho.close()
+
+
+def test_held_suarez_device_forcing_parity():
+    """BASELINE configs[4]'s forcing: hxx_held_suarez_forcing evaluated on the GPU against the oracle's C twin (and
+    through it the numpy formulas of tests/test_oracle_held_suarez.py), then six forced prim_run_subcycle_c calls.
+    log / exp / sin come from different math libraries on the two sides, so FT is held to 1e-13 instead of bit for bit;
+    the forced run to the north-star tolerance."""
+    import numpy as np
+    cfg = homme.preset("ne4", ftype=0)
+    hc, ho = parity.pair(cfg)
+    for h in (hc, ho):
+        h.run_subcycle()
+        h.held_suarez_forcing()
+    for name in ("fm", "ft"):
+        a, b = hc.get_field(name), ho.get_field(name)
+        assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max(), name
+    for _ in range(6):
+        for h in (hc, ho):
+            h.held_suarez_forcing()
+            h.run_subcycle()
+    hc.push_results(); ho.push_results()
+    sc, so = hc.state(), ho.state()
+    errs = {k: parity.rel_l2(sc[k], so[k]) for k in ("v", "T", "dp3d", "ps_v", "Qdp", "Q")}
+    print("held-suarez forced run, rel-L2 vs oracle:", errs)
+    assert max(errs.values()) <= 1e-11, errs
+    hc.close(); ho.close()

@@ -58,3 +58,24 @@ def test_held_suarez_forced_run_on_the_oracle():
     far = np.abs(u["T"] - Teq) > 20.0
     assert far.any()
     assert (np.abs(f["T"] - Teq)[far]).mean() < (np.abs(u["T"] - Teq)[far]).mean()
+
+
+def test_oracle_hs_forcing_entry_point_matches_the_numpy_formulas():
+    """hxx_held_suarez_forcing (the checker of the product's device kernel) against the numpy restatement above."""
+    cfg = homme.preset("prtcA", qsize=0, ftype=0)
+    h = homme.Homme(cfg, oraclelib.ORACLE_LIB)
+    h.init_dycore()
+    h.run_subcycle()
+    h.push_results()
+    n0 = h.time_levels()[2] - 1
+    st = h.state()
+    lat = h.array("lat").reshape(h.nelemd, 4, 4)
+    ft, _ = hs.hs_T_forcing(h.vcoord[2], h.vcoord[3], st["ps_v"][:, n0], st["T"][:, n0], lat)
+    fm = hs.hs_v_forcing(h.vcoord[2], h.vcoord[3], st["v"][:, n0])
+    h.held_suarez_forcing()
+    n, nlev = h.nelemd, cfg.nlev
+    got_ft = h.get_field("ft").reshape(n, 16, nlev).transpose(0, 2, 1).reshape(n, nlev, 4, 4)
+    got_fm = h.get_field("fm").reshape(n, 2, 16, nlev).transpose(0, 3, 1, 2).reshape(n, nlev, 2, 4, 4)
+    assert np.abs(got_ft - ft).max() <= 1e-13 * np.abs(ft).max()
+    assert np.abs(got_fm - fm).max() <= 1e-13 * np.abs(fm).max()
+    h.close()
