@@ -390,26 +390,34 @@ __global__ void minmax_pack_kernel(const int* __restrict__ send_elem, const doub
 }
 
 // elist = the elements to process (null: all, in order): elements without an off-rank neighbour
-// go first, overlapping the halo exchange the others wait for
-__global__ void minmax_kernel(const int* __restrict__ nbr8, const double* __restrict__ qin, double* __restrict__ qout,
-                              const double* __restrict__ halo, int qsize, const int* __restrict__ elist) {
-  const int ie = elist ? elist[blockIdx.x] : blockIdx.x, q = blockIdx.y;
-  for (int k = threadIdx.x; k < NLEV; k += blockDim.x) {
-    const double* mine = qin + ((size_t)ie * QSIZE_D + q) * 2 * NLEV;
-    double mn = mine[k], mx = mine[NLEV + k];
+// go first, overlapping the halo exchange the others wait for.
+// A block takes MM_E consecutive elements of the list — neighbours on the space-filling curve, so most of the
+// eight neighbours' rows a thread reads are rows other threads of the block read too — and one tracer: the
+// pass reads every qlim row nine times, and it is the L1 that absorbs the repeats instead of the L2.
+#ifndef HXX_MM_E
+#define HXX_MM_E 8
+#endif
+constexpr int MM_E = HXX_MM_E;
+__global__ void __launch_bounds__(MM_E* NLEV)
+    minmax_kernel(const int* __restrict__ nbr8, const double* qin, double* __restrict__ qout, const double* halo,
+                  int qsize, const int* __restrict__ elist, int nlist) {
+  const int el = blockIdx.x * MM_E + threadIdx.x / NLEV, k = threadIdx.x % NLEV, q = blockIdx.y;
+  if (el >= nlist) return;
+  const int ie = elist ? elist[el] : el;
+  const double* mine = qin + ((size_t)ie * QSIZE_D + q) * 2 * NLEV;
+  double mn = mine[k], mx = mine[NLEV + k];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int nb = nbr8[ie * 8 + c];
-      if (nb == DSS_NONE) continue;
-      const double* th = nb >= 0 ? qin + ((size_t)nb * QSIZE_D + q) * 2 * NLEV
-                                 : halo + ((size_t)(~nb) * qsize + q) * 2 * NLEV;
-      mn = fmin(mn, th[k]);
-      mx = fmax(mx, th[NLEV + k]);
-    }
-    double* o = qout + ((size_t)ie * QSIZE_D + q) * 2 * NLEV;
-    o[k] = mn;
-    o[NLEV + k] = mx;
+  for (int c = 0; c < 8; ++c) {
+    const int nb = nbr8[ie * 8 + c];
+    if (nb == DSS_NONE) continue;
+    const double* th = nb >= 0 ? qin + ((size_t)nb * QSIZE_D + q) * 2 * NLEV
+                               : halo + ((size_t)(~nb) * qsize + q) * 2 * NLEV;
+    mn = fmin(mn, th[k]);
+    mx = fmax(mx, th[NLEV + k]);
   }
+  double* o = qout + ((size_t)ie * QSIZE_D + q) * 2 * NLEV;
+  o[k] = mn;
+  o[NLEV + k] = mx;
 }
 
 // ---- plan ---------------------------------------------------------------------------------
@@ -947,15 +955,17 @@ void minmax_exchange() {
   }
   PROBE(K_MINMAX);
   if (!halo) {
-    minmax_kernel<<<dim3(S.nelemd, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, nullptr, nq, nullptr);
+    minmax_kernel<<<dim3((S.nelemd + MM_E - 1) / MM_E, nq), MM_E * NLEV, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, nullptr, nq,
+                                                                                       nullptr, S.nelemd);
   } else {
     // elements whose eight neighbours are on this rank first, the others once the halo has landed
     if (S.n_interior)
-      minmax_kernel<<<dim3(S.n_interior, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, recv, nq, S.elem_order);
+      minmax_kernel<<<dim3((S.n_interior + MM_E - 1) / MM_E, nq), MM_E * NLEV, 0, S.stream>>>(
+          S.nbr8, S.qlim, S.qlim_x, recv, nq, S.elem_order, S.n_interior);
     halo_arrived();
     if (S.nelemd > S.n_interior)
-      minmax_kernel<<<dim3(S.nelemd - S.n_interior, nq), 96, 0, S.stream>>>(S.nbr8, S.qlim, S.qlim_x, recv, nq,
-                                                                            S.elem_order + S.n_interior);
+      minmax_kernel<<<dim3((S.nelemd - S.n_interior + MM_E - 1) / MM_E, nq), MM_E * NLEV, 0, S.stream>>>(
+          S.nbr8, S.qlim, S.qlim_x, recv, nq, S.elem_order + S.n_interior, S.nelemd - S.n_interior);
   }
   KERNEL_LAUNCHED(K_MINMAX);
   std::swap(S.qlim, S.qlim_x);
