@@ -395,7 +395,7 @@ __global__ void minmax_pack_kernel(const int* __restrict__ send_elem, const doub
 // eight neighbours' rows a thread reads are rows other threads of the block read too — and one tracer: the
 // pass reads every qlim row nine times, and it is the L1 that absorbs the repeats instead of the L2.
 #ifndef HXX_MM_E
-#define HXX_MM_E 8
+#define HXX_MM_E 4
 #endif
 constexpr int MM_E = HXX_MM_E;
 __global__ void __launch_bounds__(MM_E* NLEV)

@@ -173,30 +173,33 @@ def load_dycore(path) -> C.CDLL:
     lib.hommexx_b200_backend.restype = C.c_char_p
     lib.hommexx_b200_launch_count.restype = C.c_int64
     lib.hommexx_b200_set_comm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
-    lib.hxx_caar_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
-    lib.hxx_rk_combine.argtypes = [C.c_int, C.c_int]
-    lib.hxx_hypervis_run.argtypes = [C.c_int, C.c_double, C.c_double]
-    lib.hxx_euler_step.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
-    lib.hxx_euler_qdp_time_avg.argtypes = [C.c_int, C.c_int]
-    lib.hxx_vertical_remap.argtypes = [C.c_int, C.c_int, C.c_double]
-    lib.hxx_update_q.argtypes = [C.c_int, C.c_int]
-    lib.hxx_prim_step_init.argtypes = [C.c_int]
-    lib.hxx_apply_forcing.argtypes = [C.c_double]
-    lib.hxx_apply_forcing.restype = None
-    lib.hxx_held_suarez_forcing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.hxx_held_suarez_forcing.restype = None
-    lib.hxx_diagnostics.argtypes = [C.c_int, C.c_int, C.c_int]
-    lib.hxx_diagnostics.restype = None
-    lib.hxx_exchange.argtypes = [C.c_char_p, C.c_int]
-    lib.hxx_get_field.argtypes = [C.c_char_p, C.c_void_p]
-    lib.hxx_get_field.restype = C.c_int64
-    lib.hxx_set_field.argtypes = [C.c_char_p, C.c_void_p]
-    lib.hxx_set_field.restype = C.c_int64
-    lib.hxx_sphere_op.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double]
-    lib.hxx_limiter.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.hxx_remap_columns.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-    for f in ("hxx_euler_reset", "hxx_euler_precompute_divdp", "hommexx_b200_sync", "finalize_hommexx_session"):
-        getattr(lib, f).restype = None
+    # section C (phase-level hooks): every product / oracle library has them; the reference's own build under
+    # oracle/_ref exports sections A and B only
+    sigs = {
+        "hxx_caar_run": ([C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int], None),
+        "hxx_rk_combine": ([C.c_int, C.c_int], None),
+        "hxx_hypervis_run": ([C.c_int, C.c_double, C.c_double], None),
+        "hxx_euler_step": ([C.c_int, C.c_int, C.c_double, C.c_double, C.c_int], None),
+        "hxx_euler_qdp_time_avg": ([C.c_int, C.c_int], None),
+        "hxx_vertical_remap": ([C.c_int, C.c_int, C.c_double], None),
+        "hxx_update_q": ([C.c_int, C.c_int], None),
+        "hxx_prim_step_init": ([C.c_int], None),
+        "hxx_apply_forcing": ([C.c_double], None),
+        "hxx_held_suarez_forcing": ([C.c_void_p, C.c_void_p, C.c_void_p], None),
+        "hxx_diagnostics": ([C.c_int, C.c_int, C.c_int], None),
+        "hxx_exchange": ([C.c_char_p, C.c_int], None),
+        "hxx_get_field": ([C.c_char_p, C.c_void_p], C.c_int64),
+        "hxx_set_field": ([C.c_char_p, C.c_void_p], C.c_int64),
+        "hxx_sphere_op": ([C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double], None),
+        "hxx_limiter": ([C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], None),
+        "hxx_remap_columns": ([C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p], None),
+        "hxx_euler_reset": ([], None), "hxx_euler_precompute_divdp": ([], None),
+        "hommexx_b200_sync": ([], None), "finalize_hommexx_session": ([], None),
+    }
+    for name, (argtypes, restype) in sigs.items():
+        if hasattr(lib, name):
+            f = getattr(lib, name)
+            f.argtypes, f.restype = argtypes, restype
     return lib
 
 
