@@ -156,20 +156,33 @@ def step_bytes_per_elem_step(cfg):
     return (caar + hvt + euler + remap + updq + misc) * F_BYTES
 
 
-def native_oracle():
-    """The timing build of the CPU port: oracle.c compiled ON THIS HOST with -O3 -march=native (BASELINE.md
-    section 3; `make -C oracle native` -> oracle/_native/, git-ignored). The parity tests keep using the strict
-    liboracle.so; this one is only ever timed. Falls back to the strict build if the compile fails."""
+def cpu_arm_library():
+    """What bench.py's CPU arm times, best first:
+    1. kind "reference": oracle/_ref/libref_hommexx_72_40_omp.so — the reference's own src/share/cxx sources in its
+       production CPU configuration (AVX2 vector packs, OpenMP over elements), built by oracle/Makefile (ref_timing)
+       against the Kokkos stand-in of oracle/ref_shim; prebuilt where /root/reference exists, it travels with the snapshot.
+    2. kind "port": the oracle compiled ON THIS HOST with -O3 -march=native (make -C oracle native), else the strict
+       parity build of the oracle."""
     from oracle import oraclelib
+    ref = ROOT / "oracle" / "_ref" / "libref_hommexx_72_40_omp.so"
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        flags = ""
+    if ref.exists() and " avx2" in flags and " fma" in flags and not os.environ.get("HXX_CPU_ARM_PORT"):
+        return ref, "reference", ("the reference's own src/share/cxx sources (CaarFunctorImpl, EulerStepFunctorImpl, "
+                                  "HyperviscosityFunctorImpl, RemapFunctor, BoundaryExchange, prim_driver ...) compiled "
+                                  "with g++ -O3 -mavx2 -mfma -fopenmp, HOMMEXX_AVX_VERSION 2 (vector packs of 4 levels), "
+                                  "against oracle/ref_shim's OpenMP Kokkos stand-in")
     out = ROOT / "oracle" / "_native" / "liboracle_native.so"
     try:
         subprocess.run(["make", "-s", "-C", str(ROOT / "oracle"), "native"], check=True, stdout=subprocess.DEVNULL,
                        stderr=subprocess.DEVNULL, timeout=300)
         if out.exists():
-            return out, "gcc -O3 -march=native -ffp-contract=fast -fopenmp (built on this host)"
+            return out, "port", "oracle port, gcc -O3 -march=native -ffp-contract=fast -fopenmp (built on this host)"
     except (OSError, subprocess.SubprocessError):
         pass
-    return oraclelib.ORACLE_LIB, "gcc -O3 -mavx2 -ffp-contract=off -fopenmp (strict parity build)"
+    return oraclelib.ORACLE_LIB, "port", "oracle port, gcc -O3 -mavx2 -ffp-contract=off -fopenmp (strict parity build)"
 
 
 def cpu_sample_mesh(args, cores):
@@ -189,7 +202,7 @@ def run_reference(args):
     os.environ["OMP_NUM_THREADS"] = str(cores)   # torchrun exports OMP_NUM_THREADS=1 to its workers
     os.environ.setdefault("OMP_PROC_BIND", "false")
     from hommexx_b200 import homme
-    lib, flags = native_oracle()
+    lib, kind, flags = cpu_arm_library()
     cfg = workload(args, 1)
     ne_s = cpu_sample_mesh(args, cores)
     cfg = workload(args, 1)
@@ -204,7 +217,7 @@ def run_reference(args):
         h.run_subcycle()
     dt = time.perf_counter() - t0
     val = h.nelem * dyn * args.steps / dt
-    sample = (f"oracle port (CPU restatement of the reference functors, {flags}), OpenMP over elements on "
+    sample = (f"{flags}; OpenMP over elements on "
               f"{cores} host threads, ne={ne_s} ({h.nelem} elements) nlev {scfg.nlev} qsize {scfg.qsize}, "
               f"homme-ne30-v1.nl namelist, {args.steps} prim_run_subcycle_c calls after {args.warmup} warm-up")
     h.close()
@@ -214,7 +227,7 @@ def run_reference(args):
            "sypd": None,
            "config": {"workload": f"preqx ne{cfg.ne} nlev{cfg.nlev} qsize{cfg.qsize}", "sample": sample,
                       "same_config": ne_s == cfg.ne},
-           "cpu_baseline": {"value": val, "unit": "element-steps/s", "cores": cores, "kind": "port", "sample": sample,
+           "cpu_baseline": {"value": val, "unit": "element-steps/s", "cores": cores, "kind": kind, "sample": sample,
                             "same_config": ne_s == cfg.ne},
            "e2e": {"value": val, "unit": "element-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -486,7 +499,7 @@ def main():
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         os.environ["OMP_NUM_THREADS"] = str(cores)
-        olib, flags = native_oracle()
+        olib, kind, flags = cpu_arm_library()
         ne_s = cpu_sample_mesh(args, cores)
         scfg = homme.preset("ne30", ne=ne_s, qsize=cfg.qsize)
         ho = homme.Homme(scfg, olib)
@@ -497,9 +510,9 @@ def main():
         for _ in range(nrep):
             ho.run_subcycle()
         dt = time.perf_counter() - t0
-        cpu = {"value": ho.nelem * dyn * nrep / dt, "unit": "element-steps/s", "cores": cores, "kind": "port",
+        cpu = {"value": ho.nelem * dyn * nrep / dt, "unit": "element-steps/s", "cores": cores, "kind": kind,
                "same_config": ne_s == cfg.ne,
-               "sample": f"oracle port ({flags}), {nrep} prim_run_subcycle_c calls at ne={ne_s} ({ho.nelem} elements), "
+               "sample": f"{flags}; {nrep} prim_run_subcycle_c calls at ne={ne_s} ({ho.nelem} elements), "
                          f"nlev {scfg.nlev}, qsize {scfg.qsize}, OpenMP over elements on {cores} host threads"}
         ho.close()
 

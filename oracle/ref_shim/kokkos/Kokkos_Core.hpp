@@ -25,6 +25,17 @@
 #include <utility>
 
 #define KOKKOS_ENABLE_SERIAL
+// REF_SHIM_OPENMP (the timing build only, bench.py's CPU arm): league iterations and flat ranges are spread over the
+// host threads with OpenMP, as Kokkos' own OpenMP back end does with one thread per team; everything inside a team
+// stays sequential. The parity builds never define it.
+#ifdef REF_SHIM_OPENMP
+#include <omp.h>
+#define KOKKOS_ENABLE_OPENMP
+#define REF_SHIM_PRAGMA(x) _Pragma(#x)
+#define REF_SHIM_PARALLEL_FOR REF_SHIM_PRAGMA(omp parallel for schedule(static))
+#else
+#define REF_SHIM_PARALLEL_FOR
+#endif
 #define KOKKOS_INLINE_FUNCTION inline
 #define KOKKOS_FORCEINLINE_FUNCTION inline __attribute__((always_inline))
 #define KOKKOS_FUNCTION
@@ -61,8 +72,26 @@ struct Serial {
   static const char* name() { return "Serial (reference shim)"; }
   static void print_configuration(std::ostream&, bool = false) {}
 };
+#ifdef REF_SHIM_OPENMP
+struct OpenMP {
+  using execution_space = OpenMP;
+  using memory_space = HostSpace;
+  using scratch_memory_space = ScratchMemorySpace;
+  using array_layout = LayoutRight;
+  using device_type = OpenMP;
+  static int concurrency() { return omp_get_max_threads(); }
+  static int impl_thread_pool_size() { return omp_get_max_threads(); }
+  static int thread_pool_size() { return omp_get_max_threads(); }
+  static void fence() {}
+  static const char* name() { return "OpenMP (reference shim)"; }
+  static void print_configuration(std::ostream&, bool = false) {}
+};
+using DefaultExecutionSpace = OpenMP;
+using DefaultHostExecutionSpace = OpenMP;
+#else
 using DefaultExecutionSpace = Serial;
 using DefaultHostExecutionSpace = Serial;
+#endif
 
 enum MemoryTraitsFlags { Unmanaged = 0x01, RandomAccess = 0x02, Atomic = 0x04, Restrict = 0x08, Aligned = 0x10 };
 template <unsigned T>
@@ -209,9 +238,20 @@ class View {
   template <class... Ints>
   explicit View(const std::string& label, Ints... n) : m_label(label) {
     set_extents(n...);
+    // 64-byte aligned and value-initialised, as Kokkos allocations are (the AVX vector packs need the alignment)
     const size_t cnt = span();
-    non_const_value_type* p = cnt ? new non_const_value_type[cnt]() : nullptr;
-    m_owner = std::shared_ptr<void>(p, [](void* q) { delete[] static_cast<non_const_value_type*>(q); });
+    non_const_value_type* p = nullptr;
+    if (cnt) {
+      void* raw = nullptr;
+      if (posix_memalign(&raw, Impl::MEMORY_ALIGNMENT, cnt * sizeof(non_const_value_type)) != 0) std::abort();
+      p = static_cast<non_const_value_type*>(raw);
+      for (size_t i = 0; i < cnt; ++i) new (p + i) non_const_value_type();
+    }
+    m_owner = std::shared_ptr<void>(p, [cnt](void* q) {
+      non_const_value_type* t = static_cast<non_const_value_type*>(q);
+      for (size_t i = 0; i < cnt; ++i) t[i].~non_const_value_type();
+      std::free(q);
+    });
     m_ptr = p;
   }
   explicit View(const char* label) : View(std::string(label)) {}
@@ -403,7 +443,8 @@ template <class... Args>
 struct FindTag { using type = void; };
 template <class A, class... Args>
 struct FindTag<A, Args...> {
-  using type = typename std::conditional<std::is_same<A, Serial>::value || std::is_void<A>::value,
+  using type = typename std::conditional<std::is_same<A, Serial>::value || std::is_same<A, DefaultExecutionSpace>::value ||
+                                             std::is_void<A>::value,
                                          typename FindTag<Args...>::type, A>::type;
 };
 template <class T, class... Args>
@@ -540,21 +581,29 @@ KOKKOS_FORCEINLINE_FUNCTION void single(const Impl::TeamSingle&, const F& f) { f
 template <class... A, class F>
 void parallel_for(const TeamPolicy<A...>& p, const F& f) {
   using Tag = typename TeamPolicy<A...>::work_tag;
-  for (int l = 0; l < p.league_size(); ++l) Impl::call<Tag>(f, Impl::TeamMember{l, p.league_size()});
+  const int n = p.league_size();
+  REF_SHIM_PARALLEL_FOR
+  for (int l = 0; l < n; ++l) Impl::call<Tag>(f, Impl::TeamMember{l, n});
 }
 template <class... A, class F>
 void parallel_for(const RangePolicy<A...>& p, const F& f) {
   using Tag = typename RangePolicy<A...>::work_tag;
-  for (long i = p.begin(); i < p.end(); ++i) Impl::call<Tag>(f, int(i));
+  const long b = p.begin(), e = p.end();
+  REF_SHIM_PARALLEL_FOR
+  for (long i = b; i < e; ++i) Impl::call<Tag>(f, int(i));
 }
 template <class Space, class O, class I, class... R, class F>
 void parallel_for(const Experimental::MDRangePolicy<Space, Experimental::Rank<2, O, I>, R...>& p, const F& f) {
-  for (long i = p.m_lo[0]; i < p.m_hi[0]; ++i)
+  const long lo0 = p.m_lo[0], hi0 = p.m_hi[0];
+  REF_SHIM_PARALLEL_FOR
+  for (long i = lo0; i < hi0; ++i)
     for (long j = p.m_lo[1]; j < p.m_hi[1]; ++j) f(int(i), int(j));
 }
 template <class Space, class O, class I, class... R, class F>
 void parallel_for(const Experimental::MDRangePolicy<Space, Experimental::Rank<3, O, I>, R...>& p, const F& f) {
-  for (long i = p.m_lo[0]; i < p.m_hi[0]; ++i)
+  const long lo0 = p.m_lo[0], hi0 = p.m_hi[0];
+  REF_SHIM_PARALLEL_FOR
+  for (long i = lo0; i < hi0; ++i)
     for (long j = p.m_lo[1]; j < p.m_hi[1]; ++j)
       for (long k = p.m_lo[2]; k < p.m_hi[2]; ++k) f(int(i), int(j), int(k));
 }

@@ -88,3 +88,21 @@ def test_diagnostics_match_the_reference_build():
     ora = run(cfg, oraclelib.ORACLE_LIB, 9, diagnostics=True)
     for k in ref:
         assert np.array_equal(ref[k], ora[k]), (k, float(np.abs(ref[k] - ora[k]).max()))
+
+
+def test_reference_timing_build_agrees_with_its_serial_build():
+    """oracle/_ref/libref_hommexx_72_40_omp.so is what bench.py's CPU arm times: the same sources with AVX2 vector packs,
+    FMA contraction and OpenMP over elements. It must agree with the serial scalar build to round-off (north-star
+    tolerance 1e-11) — which also checks that the stand-in's thread-parallel league loop races on nothing."""
+    import os
+    from reference_lib import REF_DIR
+    omp = REF_DIR / "libref_hommexx_72_40_omp.so"
+    if not omp.exists() or " avx2" not in open("/proc/cpuinfo").read():
+        pytest.skip("timing build of the reference absent (or no AVX2 on this host)")
+    os.environ.setdefault("OMP_NUM_THREADS", str(min(8, os.cpu_count() or 1)))
+    cfg = homme.preset("ne4", qsize=40, qsize_d=40)
+    a = run(cfg, omp)
+    b = run(cfg, reference_lib(72, 40))
+    for k in ("v", "T", "dp3d", "ps_v", "Qdp", "Q"):
+        err = np.sqrt(((a[k] - b[k]) ** 2).sum()) / np.sqrt((b[k] ** 2).sum())
+        assert err <= 1e-11, (k, err)
