@@ -19,8 +19,10 @@ __global__ void rmw(double2* __restrict__ buf, const int* __restrict__ order, lo
   buf[dst] = x;
 }
 
-int main() {
-  const size_t bytes = size_t(4) << 30;
+int main(int argc, char** argv) {
+  // default 4 GiB (HBM behaviour); a size below the 126 MB L2 (e.g. 48) shows what the same pass costs on L2-resident data
+  const size_t bytes = argc > 1 ? size_t(atol(argv[1])) << 20 : size_t(4) << 30;
+  printf("buffer %zu MiB\n", bytes >> 20);
   double2* buf;
   cudaMalloc(&buf, bytes);
   cudaMemset(buf, 0, bytes);
@@ -44,7 +46,7 @@ int main() {
       const long long nthreads = (long long)order.size() * vpc;
       const int nb = (int)((nthreads + 127) / 128);
       float best = 1e30f;
-      for (int rep = 0; rep < 5; ++rep) {
+      for (int rep = 0; rep < 8; ++rep) {
         cudaEventRecord(a);
         rmw<<<nb, 128>>>(buf, d_order, (long long)order.size(), vpc);
         cudaEventRecord(b);
