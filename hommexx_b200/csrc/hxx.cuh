@@ -124,6 +124,8 @@ struct Session {
   void* nccl = nullptr;  // ncclComm_t
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t comm_stream = nullptr;  // halo pack + NCCL transfers (multi-GPU)
+  cudaStream_t copy_stream = nullptr;  // PCIe copies of the Fortran-layout arrays (overlapped with their transposes)
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_xpose[2] = {nullptr, nullptr};
   cudaEvent_t ev_produced = nullptr, ev_halo = nullptr;
   int64_t launches = 0;
   int64_t launches_by[K_COUNT] = {};

@@ -115,31 +115,53 @@ static void launch_transpose(const double* src, double* dst, size_t nbatch, int 
   KERNEL_LAUNCHED(K_TRANSPOSE);
 }
 
-constexpr size_t STAGE_BYTES = size_t(256) << 20;
+// Host <-> device moves of the Fortran-layout arrays go through two device staging buffers so that the PCIe copy
+// of one chunk overlaps the layout transposition of the other (copy stream <-> compute stream, one event pair per
+// buffer); with page-locked host arrays both directions then run at the bus rate instead of copy + kernel in turn.
+constexpr size_t STAGE_BYTES = size_t(128) << 20;  // per staging buffer
 
-// host F90 [b][NLEV][C] -> device [b][C][NLEV], chunked through a device staging buffer
+// host F90 [b][NLEV][C] -> device [b][C][NLEV]
 static void pull_field(const double* host, double* dev, size_t nbatch, int C) {
+  if (!nbatch) return;
   const size_t item = (size_t)NLEV * C;
   const size_t per = std::max<size_t>(1, STAGE_BYTES / (item * 8));
-  double* st = (double*)scratch(std::min(nbatch, per) * item * 8);
-  for (size_t b0 = 0; b0 < nbatch; b0 += per) {
+  const size_t half = std::min(nbatch, per) * item;
+  double* st = (double*)scratch(2 * half * 8);
+  CUDA_OK(cudaEventRecord(S.ev_xpose[0], S.stream));  // the staging buffers may still be read by earlier work
+  CUDA_OK(cudaStreamWaitEvent(S.copy_stream, S.ev_xpose[0], 0));
+  int i = 0;
+  for (size_t b0 = 0; b0 < nbatch; b0 += per, ++i) {
     const size_t nb = std::min(per, nbatch - b0);
-    CUDA_OK(cudaMemcpyAsync(st, host + b0 * item, nb * item * 8, cudaMemcpyHostToDevice, S.stream));
-    launch_transpose(st, dev + b0 * item, nb, NLEV, C);
-    CUDA_OK(cudaStreamSynchronize(S.stream));
+    const int b = i & 1;
+    if (i >= 2) CUDA_OK(cudaStreamWaitEvent(S.copy_stream, S.ev_xpose[b], 0));  // chunk i - 2 has left this buffer
+    CUDA_OK(cudaMemcpyAsync(st + b * half, host + b0 * item, nb * item * 8, cudaMemcpyHostToDevice, S.copy_stream));
+    CUDA_OK(cudaEventRecord(S.ev_copy[b], S.copy_stream));
+    CUDA_OK(cudaStreamWaitEvent(S.stream, S.ev_copy[b], 0));
+    launch_transpose(st + b * half, dev + b0 * item, nb, NLEV, C);
+    CUDA_OK(cudaEventRecord(S.ev_xpose[b], S.stream));
   }
+  CUDA_OK(cudaStreamSynchronize(S.stream));
 }
 // device [b][C][NLEV] -> host F90 [b][NLEV][C]
 static void push_field(const double* dev, double* host, size_t nbatch, int C) {
+  if (!nbatch) return;
   const size_t item = (size_t)NLEV * C;
   const size_t per = std::max<size_t>(1, STAGE_BYTES / (item * 8));
-  double* st = (double*)scratch(std::min(nbatch, per) * item * 8);
-  for (size_t b0 = 0; b0 < nbatch; b0 += per) {
+  const size_t half = std::min(nbatch, per) * item;
+  double* st = (double*)scratch(2 * half * 8);
+  int i = 0;
+  for (size_t b0 = 0; b0 < nbatch; b0 += per, ++i) {
     const size_t nb = std::min(per, nbatch - b0);
-    launch_transpose(dev + b0 * item, st, nb, C, NLEV);
-    CUDA_OK(cudaMemcpyAsync(host + b0 * item, st, nb * item * 8, cudaMemcpyDeviceToHost, S.stream));
-    CUDA_OK(cudaStreamSynchronize(S.stream));
+    const int b = i & 1;
+    if (i >= 2) CUDA_OK(cudaStreamWaitEvent(S.stream, S.ev_copy[b], 0));  // chunk i - 2 has reached the host
+    launch_transpose(dev + b0 * item, st + b * half, nb, C, NLEV);
+    CUDA_OK(cudaEventRecord(S.ev_xpose[b], S.stream));
+    CUDA_OK(cudaStreamWaitEvent(S.copy_stream, S.ev_xpose[b], 0));
+    CUDA_OK(cudaMemcpyAsync(host + b0 * item, st + b * half, nb * item * 8, cudaMemcpyDeviceToHost, S.copy_stream));
+    CUDA_OK(cudaEventRecord(S.ev_copy[b], S.copy_stream));
   }
+  CUDA_OK(cudaStreamSynchronize(S.copy_stream));
+  CUDA_OK(cudaStreamSynchronize(S.stream));
 }
 
 void* diag_scratch(size_t bytes) {
@@ -382,6 +404,11 @@ void initialize_hommexx_session(void) {
     CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CUDA_OK(cudaStreamCreateWithPriority(&S.comm_stream, cudaStreamNonBlocking, hi));
   }
+  CUDA_OK(cudaStreamCreateWithFlags(&S.copy_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    CUDA_OK(cudaEventCreateWithFlags(&S.ev_copy[b], cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&S.ev_xpose[b], cudaEventDisableTiming));
+  }
   CUDA_OK(cudaEventCreateWithFlags(&S.ev_produced, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&S.ev_halo, cudaEventDisableTiming));
   S.active = true;
@@ -402,6 +429,12 @@ void finalize_hommexx_session(void) {
 #endif
   CUDA_OK(cudaStreamDestroy(S.stream));
   CUDA_OK(cudaStreamDestroy(S.comm_stream));
+  CUDA_OK(cudaStreamDestroy(S.copy_stream));
+  for (int b = 0; b < 2; ++b) {
+    CUDA_OK(cudaEventDestroy(S.ev_copy[b]));
+    CUDA_OK(cudaEventDestroy(S.ev_xpose[b]));
+  }
+  S.copy_stream = nullptr;
   CUDA_OK(cudaEventDestroy(S.ev_produced));
   CUDA_OK(cudaEventDestroy(S.ev_halo));
   S.stream = S.comm_stream = nullptr;
