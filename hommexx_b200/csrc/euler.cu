@@ -22,7 +22,6 @@ namespace hxx {
 struct EulerArgs {
   const double* geo;
   const double* tensorvisc;
-  const double *lapmat, *lapmat2;  // FMA build: Laplacian matrices of compute_biharmonic_pre / _post
   double *qdp, *qtens_biharmonic, *qlim;
   const double *derived_dp, *divdp_proj, *divdp, *derived_vn0, *dpdiss_ave, *dpdiss_biharmonic;
   double* f_dss;
@@ -77,13 +76,6 @@ __global__ void __launch_bounds__(BIH_T, HXX_BIH_MINB) euler_qminmax_kernel(cons
   __shared__ double s_geo[geo_span(32) * NPSQ * GEO_N];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int e_first = (int)(((long long)blockIdx.x * 32) / NLEV);
-#ifdef HXX_FMA
-  __shared__ __align__(16) double s_L[BIH ? geo_span(32) * LAPMAT_N : 2];
-  if (BIH) {
-    for (int i = threadIdx.x; i < geo_span(32) * LAPMAT_N; i += BIH_T)
-      if (e_first + i / LAPMAT_N < a.nelem) s_L[i] = __ldg(a.lapmat + (size_t)e_first * LAPMAT_N + i);
-  }
-#endif
   if (BIH) stage_geo<geo_span(32), BIH_T>(s_geo, a.geo, e_first, a.nelem);
   const long long gl = (long long)blockIdx.x * 32 + lane, glmax = (long long)a.nelem * NLEV - 1;
   const bool valid = gl <= glmax;
@@ -145,17 +137,11 @@ __global__ void __launch_bounds__(BIH_T, HXX_BIH_MINB) euler_qminmax_kernel(cons
       for (int p = 0; p < NPSQ; ++p) Q[p] = Q[p] * s_dave[p * 32];
       div_rcp_plane(Q, [&](int) { return dp0k; }, [&](int) { return rdp0k; });
     }
-    if (BIH) {
-      auto emit = [&](int p, double lap) {
+    if (BIH)
+      laplace_points<false>(g, nullptr, Q, [&](int p, double lap) {
         if (is_interior_pt(p)) lap *= geo_ld(g, p, G_RSPHEREMP);  // rspheremp of the DSS that follows
         if (valid) qtb[p * NLEV] = lap;
-      };
-#ifdef HXX_FMA
-      laplace_mat(s_L + (ie - e_first) * LAPMAT_N, Q, emit);
-#else
-      laplace_points<false>(g, nullptr, Q, emit);
-#endif
-    }
+      });
   }
   cp_async_wait<0>();
 }
@@ -206,11 +192,6 @@ __global__ void __launch_bounds__(TPB, HXX_HVPOST_MINB) euler_hvpost_kernel(cons
   extern __shared__ double s_all[];
   __shared__ double s_geo[geo_span(TPB) * NPSQ * GEO_N];
   const int e_first = (int)(((long long)blockIdx.x * TPB) / NLEV);
-#ifdef HXX_FMA
-  __shared__ __align__(16) double s_L[geo_span(TPB) * LAPMAT_N];
-  for (int i = threadIdx.x; i < geo_span(TPB) * LAPMAT_N; i += TPB)
-    if (e_first + i / LAPMAT_N < a.nelem) s_L[i] = __ldg(a.lapmat2 + (size_t)e_first * LAPMAT_N + i);
-#endif
   stage_geo<geo_span(TPB), TPB>(s_geo, a.geo, e_first, a.nelem);
   int ie, k;
   if (!map_thread(a.nelem, ie, k)) return;
@@ -240,12 +221,7 @@ __global__ void __launch_bounds__(TPB, HXX_HVPOST_MINB) euler_hvpost_kernel(cons
     prefetch(q + 2, buf);
     double t[NPSQ];
     auto emit = [&](int p, double lap) { t[p] = bfac * dp0k * lap; };
-#ifdef HXX_FMA
-    (void)tv;
-    laplace_mat(s_L + (ie - e_first) * LAPMAT_N, s, emit);
-#else
     if (a.consthv) laplace_points<false>(g, tv, s, emit); else laplace_points<true>(g, tv, s, emit);
-#endif
     div_rcp_plane(t, [&](int p) { return geo_ld(g, p, G_SPHEREMP); }, [&](int p) { return geo_ld(g, p, G_INV_SPHEREMP); });
     plane_store(qtb + (size_t)q * NLF, t);
   }
@@ -506,8 +482,7 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   if (!S.nelemd || !nq) return;
   const int mode = rhs_multiplier == 0.0 ? 0 : rhs_multiplier == 1.0 ? 1 : 2;
   if (mode == 2) S.rhs_viss = 3.0;  // compute_biharmonic_pre :196-214
-  if (mode == 2) ensure_lapmat();
-  EulerArgs a{S.geo, S.tensorvisc, S.lapmat, S.p.consthv ? S.lapmat : S.lapmat_tensor, S.qdp, S.qtens_biharmonic, S.qlim, S.derived_dp, S.divdp_proj, S.divdp,
+  EulerArgs a{S.geo, S.tensorvisc, S.qdp, S.qtens_biharmonic, S.qlim, S.derived_dp, S.divdp_proj, S.divdp,
               S.derived_vn0, S.dpdiss_ave, S.dpdiss_biharmonic, dss_var(dss_opt), S.nelemd, nq, tracer_chunk(),
               n0_qdp, np1_qdp, dt, rhs_multiplier * dt, S.p.nu_p, S.p.nu_q, S.rhs_viss, mode, tavg_n0_qdp, S.p.limiter_option,
               S.p.consthv ? 1 : 0};

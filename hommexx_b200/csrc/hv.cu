@@ -20,7 +20,6 @@ namespace hxx {
 #endif
 struct HvArgs {
   const double *geo, *metinv, *tensorvisc, *vec_sph2cart;
-  const double *lapmat, *lapmat2;  // FMA build: Laplacian matrices of the first / second application (simple; simple or tensor)
   double *v, *t, *dp3d, *vtens, *ttens, *dptens, *dpdiss_ave, *dpdiss_biharmonic;
   int nelem, np1;
   double dt, eta_ave_w, nu, nu_s, nu_p, nu_top, nu_ratio1, nu_ratio2;
@@ -61,13 +60,11 @@ __global__ void __launch_bounds__(TPB, HXX_HV_MINB) hv_first_laplace_kernel(cons
   if (!map_thread(a.nelem, ie, k)) return;
   const GeoShared g{s_geo + (ie - e_first) * NPSQ * GEO_N};
   const GeoShared mi{s_mi + (ie - e_first) * 4 * NPSQ};
-  // (the matrix form of the FMA build is not used here: next to the vector Laplacian it made this kernel spill)
-#define HXX_LAPLACE_SIMPLE(S_, EMIT_) laplace_points<false>(g, nullptr, S_, EMIT_)
   {
     double s[NPSQ];
     plane_load(a.t + off_s(ie, a.np1) + k, s);
     double* out = a.ttens + off_f(ie) + k;
-    HXX_LAPLACE_SIMPLE(s, [&](int p, double lap) {
+    laplace_points<false>(g, nullptr, s, [&](int p, double lap) {
       if (is_interior_pt(p)) lap *= geo_ld(g, p, G_RSPHEREMP);
       out[p * NLEV] = lap;
     });
@@ -77,12 +74,11 @@ __global__ void __launch_bounds__(TPB, HXX_HV_MINB) hv_first_laplace_kernel(cons
     double s[NPSQ];
     plane_load(a.dp3d + off_s(ie, a.np1) + k, s);
     double* out = a.dptens + off_f(ie) + k;
-    HXX_LAPLACE_SIMPLE(s, [&](int p, double lap) {
+    laplace_points<false>(g, nullptr, s, [&](int p, double lap) {
       if (is_interior_pt(p)) lap *= geo_ld(g, p, G_RSPHEREMP);
       out[p * NLEV] = lap;
     });
   }
-#undef HXX_LAPLACE_SIMPLE
   phase_fence();
   double* o0 = a.vtens + ((size_t)ie * 2 + 0) * NLF + k;
   double* o1 = a.vtens + ((size_t)ie * 2 + 1) * NLF + k;
@@ -124,25 +120,13 @@ __global__ void __launch_bounds__(TPB, SPONGE ? 2 : 3) hv_second_scalar_kernel(c
   // the main (non-sponge) instantiation walks >= NLEV - 3 levels per element, so a block spans
   // at most HV2_SPAN elements and reads their geometry from shared memory
   __shared__ double s_geo[SPONGE ? 1 : HV2_SPAN * NPSQ * GEO_N];
-#ifdef HXX_FMA
-  __shared__ __align__(16) double s_L[SPONGE ? 2 : HV2_SPAN * LAPMAT_N];
-#endif
   const int e_first = SPONGE ? 0 : (int)(((long long)blockIdx.x * TPB) / (NLEV - nsponge));
-#ifdef HXX_FMA
-  if (!SPONGE) stage_records<HV2_SPAN, LAPMAT_N, TPB>(s_L, a.lapmat2, e_first, a.nelem);
-#endif
   if (!SPONGE) stage_geo<HV2_SPAN, TPB>(s_geo, a.geo, e_first, a.nelem);
   int ie, k;
   if (!map_thread_hv2<SPONGE>(a.nelem, nsponge, ie, k)) return;
   using Geo = typename std::conditional<SPONGE, GeoGlobal, GeoShared>::type;
   const Geo g{SPONGE ? a.geo + (size_t)ie * NPSQ * GEO_N : s_geo + (ie - e_first) * NPSQ * GEO_N};
   const double* __restrict__ tv = a.consthv ? nullptr : a.tensorvisc + (size_t)ie * 4 * NPSQ;
-#ifdef HXX_FMA
-  // the three sponge levels read the matrices from global memory (L1), the rest from the block's copy
-  const double* const L2nd = SPONGE ? a.lapmat2 + (size_t)ie * LAPMAT_N : s_L + (ie - e_first) * LAPMAT_N;
-  const double* const L1st = a.lapmat + (size_t)ie * LAPMAT_N;
-  (void)tv; (void)L1st;
-#endif
   const double nst = (k == 0 ? 4.0 : k == 1 ? 2.0 : 1.0) * a.nu_top;  // HyperviscosityFunctorImpl.cpp:24-38
   {  // T
     double* tt = a.ttens + off_f(ie) + k;
@@ -151,22 +135,14 @@ __global__ void __launch_bounds__(TPB, SPONGE ? 2 : 3) hv_second_scalar_kernel(c
     if constexpr (SPONGE) {
       double t[NPSQ];
       plane_load(a.t + off_s(ie, a.np1) + k, t);
-#ifdef HXX_FMA
-      laplace_mat(L1st, t, [&](int p, double lap) { top[p] = lap; });
-#else
       laplace_simple(g, t, top);
-#endif
     }
     auto emit = [&](int p, double lap) {
       lap *= -a.nu_s;
       if constexpr (SPONGE) lap += nst * top[p];
       tt[p * NLEV] = lap;
     };
-#ifdef HXX_FMA
-    laplace_mat(L2nd, s, emit);
-#else
     if (a.consthv) laplace_points<false>(g, tv, s, emit); else laplace_points<true>(g, tv, s, emit);
-#endif
   }
   phase_fence();
   {  // dp3d
@@ -187,11 +163,7 @@ __global__ void __launch_bounds__(TPB, SPONGE ? 2 : 3) hv_second_scalar_kernel(c
       for (int p = 0; p < NPSQ; ++p) r0[p] += t[p];
       plane_store(dave, r0);
     }
-#ifdef HXX_FMA
-    if constexpr (SPONGE) laplace_mat(L1st, dp, [&](int p, double lap) { top[p] = lap; });
-#else
     if constexpr (SPONGE) laplace_simple(g, dp, top);
-#endif
     double s[NPSQ], r1[NPSQ];
     plane_load(dt_, s);
     plane_load(dbih, r1);
@@ -204,11 +176,7 @@ __global__ void __launch_bounds__(TPB, SPONGE ? 2 : 3) hv_second_scalar_kernel(c
       lap += dp[p] * geo_ld(g, p, G_SPHEREMP);
       dt_[p * NLEV] = lap;
     };
-#ifdef HXX_FMA
-    laplace_mat(L2nd, s, emit);
-#else
     if (a.consthv) laplace_points<false>(g, tv, s, emit); else laplace_points<true>(g, tv, s, emit);
-#endif
   }
 }
 
@@ -307,44 +275,10 @@ __global__ void hv_update_states_kernel(const HvArgs a) {
   }
 }
 
-#ifdef HXX_FMA
-// lapmat[ie][p][q] = (Laplacian of the unit vector e_q) at point p: one thread per (element, q)
-template <bool TENSOR>
-__global__ void build_lapmat_kernel(const double* __restrict__ geo, const double* __restrict__ tensorvisc,
-                                    double* __restrict__ lapmat, int nelem) {
-  const int ie = blockIdx.x, q = threadIdx.x;
-  if (ie >= nelem || q >= NPSQ) return;
-  const GeoGlobal g{geo + (size_t)ie * NPSQ * GEO_N};
-  const double* tv = TENSOR ? tensorvisc + (size_t)ie * 4 * NPSQ : nullptr;
-  double s[NPSQ];
-  HXX_UNROLL
-  for (int p = 0; p < NPSQ; ++p) s[p] = (p == q) ? 1.0 : 0.0;
-  double* out = lapmat + (size_t)ie * LAPMAT_N + q;
-  laplace_points<TENSOR>(g, tv, s, [&](int p, double lap) { out[p * NPSQ] = lap; });
-}
-#endif
-
-void ensure_lapmat() {
-#ifdef HXX_FMA
-  if (S.lapmat || !S.nelemd) return;
-  CUDA_OK(cudaMalloc(&S.lapmat, (size_t)S.nelemd * LAPMAT_N * sizeof(double)));
-  PROBE(K_HOOK);
-  build_lapmat_kernel<false><<<S.nelemd, NPSQ, 0, S.stream>>>(S.geo, nullptr, S.lapmat, S.nelemd);
-  KERNEL_LAUNCHED(K_HOOK);
-  if (!S.p.consthv) {
-    CUDA_OK(cudaMalloc(&S.lapmat_tensor, (size_t)S.nelemd * LAPMAT_N * sizeof(double)));
-    PROBE(K_HOOK);
-    build_lapmat_kernel<true><<<S.nelemd, NPSQ, 0, S.stream>>>(S.geo, S.tensorvisc, S.lapmat_tensor, S.nelemd);
-    KERNEL_LAUNCHED(K_HOOK);
-  }
-#endif
-}
-
 void hypervis_run(int np1, double dt_in, double eta_ave_w) {
   if (!S.nelemd) return;
   const Params& p = S.p;
-  ensure_lapmat();
-  HvArgs a{S.geo, S.metinv, S.tensorvisc, S.vec_sph2cart, S.lapmat, p.consthv ? S.lapmat : S.lapmat_tensor, S.v, S.t, S.dp3d, S.vtens, S.ttens, S.dptens,
+  HvArgs a{S.geo, S.metinv, S.tensorvisc, S.vec_sph2cart, S.v, S.t, S.dp3d, S.vtens, S.ttens, S.dptens,
            S.dpdiss_ave, S.dpdiss_biharmonic, S.nelemd, np1, dt_in / p.hypervis_subcycle, eta_ave_w, p.nu, p.nu_s,
            p.nu_p, p.nu_top, p.nu_ratio1, p.nu_ratio2, p.hypervis_subcycle, p.consthv ? 1 : 0};
   const int nb = nblocks_flat(S.nelemd);

@@ -149,7 +149,6 @@ struct Session {
   double *vtens = nullptr, *ttens = nullptr, *dptens = nullptr;
   double *vstar = nullptr, *dpdissk = nullptr, *dp_star = nullptr;  // test-visible scratch
   double *qdp = nullptr, *qtens_biharmonic = nullptr, *qlim = nullptr, *qlim_x = nullptr, *Q = nullptr;
-  double *lapmat = nullptr, *lapmat_tensor = nullptr;  // FMA build: per-element 16 x 16 scalar-Laplacian matrices (hv.cu)
   double *hs_lat = nullptr, *hs_hyam = nullptr;  // Held-Suarez inputs: [ie][16] latitudes, [2][NLEV] hyam | hybm
   double *fm = nullptr, *ft = nullptr, *fq = nullptr;  // CAM forcing [ie][2][16][NLEV], [ie][16][NLEV], [ie][QSIZE_D][16][NLEV]
   // exchange plan
@@ -331,7 +330,6 @@ void prim_step_init(int n0);
 void update_q(int np1_qdp, int np1);
 // hv.cu
 void hypervis_run(int np1, double dt, double eta_ave_w);
-void ensure_lapmat();  // FMA build: builds S.lapmat (and S.lapmat_tensor) on first use; a no-op in the strict build
 // euler.cu
 void euler_precompute_divdp();
 // tavg_n0_qdp >= 0 fuses qdp_time_avg(tavg_n0_qdp, np1_qdp) into this stage (its advection

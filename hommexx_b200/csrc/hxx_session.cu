@@ -182,7 +182,7 @@ static void free_all() {
   dfree(S.divdp); dfree(S.divdp_proj); dfree(S.dpdiss_ave); dfree(S.dpdiss_biharmonic);
   dfree(S.vtens); dfree(S.ttens); dfree(S.dptens); dfree(S.vstar); dfree(S.dpdissk); dfree(S.dp_star);
   dfree(S.qdp); dfree(S.qtens_biharmonic); dfree(S.qlim); dfree(S.qlim_x); dfree(S.Q);
-  dfree(S.fm); dfree(S.ft); dfree(S.fq); dfree(S.hs_lat); dfree(S.hs_hyam); dfree(S.lapmat); dfree(S.lapmat_tensor);
+  dfree(S.fm); dfree(S.ft); dfree(S.fq); dfree(S.hs_lat); dfree(S.hs_hyam);
   free_exchange_plan();
   dfree(S.invalid_flag);
   if (S.h_invalid) { cudaFreeHost(S.h_invalid); S.h_invalid = nullptr; }

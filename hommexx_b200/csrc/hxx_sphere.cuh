@@ -71,10 +71,6 @@ __device__ __forceinline__ void deriv_pair(const double (&sx)[NPSQ], const doubl
   }
 }
 
-// compiler-level fence: keeps loads and stores (and with them the live ranges they start or end) on
-// their side of a phase boundary
-__device__ __forceinline__ void phase_fence() { asm volatile("" ::: "memory"); }
-
 // one point of deriv_pair (same sums, same order)
 __device__ __forceinline__ void deriv_point(const double (&sx)[NPSQ], const double (&sy)[NPSQ], int i, int j, double& a,
                                             double& b) {
@@ -95,6 +91,9 @@ __device__ __forceinline__ void gradient_point(const G& g, const double (&s)[NPS
   g0 = geo_ld(g, p, G_DINV00) * v0 + geo_ld(g, p, G_DINV01) * v1;
   g1 = geo_ld(g, p, G_DINV10) * v0 + geo_ld(g, p, G_DINV11) * v1;
 }
+// compiler-level fence: keeps loads and stores (and with them the live ranges they start or end) on
+// their side of a phase boundary
+__device__ __forceinline__ void phase_fence() { asm volatile("" ::: "memory"); }
 
 // SphereOperators.hpp:293-319
 template <class G>
@@ -489,31 +488,6 @@ __device__ __forceinline__ void vlaplace_contra_points(const G& g, const MI& mi,
     }
   }
 }
-
-#ifdef HXX_FMA
-// FMA build only. On one element the scalar weak Laplacian (laplace_simple :588-597 / laplace_tensor :604-635) is a
-// fixed linear map of the 16 point values; lapmat holds it as a 16 x 16 matrix per element, built once per session
-// by applying laplace_points to the unit vectors (hv.cu, build_lapmat_kernel). 256 fused multiply-adds per plane
-// instead of the ~540 FP64 instructions of gradient -> metric -> weak divergence; a different association of the same
-// sums, so only the build that is held to the 1e-11 tolerance (not the bit-identical one) uses it.
-template <class F>
-__device__ __forceinline__ void laplace_mat(const double* L, const double (&s)[NPSQ], F&& emit) {
-  HXX_UNROLL
-  for (int p = 0; p < NPSQ; ++p) {
-    if (p % 4 == 0) phase_fence();  // keeps ptxas from hoisting all 128 matrix loads to the top (spills)
-    const double2* row = reinterpret_cast<const double2*>(L + p * NPSQ);
-    double acc = 0.0;
-    HXX_UNROLL
-    for (int q2 = 0; q2 < NPSQ / 2; ++q2) {
-      const double2 l = row[q2];
-      acc = fma(l.x, s[2 * q2], acc);
-      acc = fma(l.y, s[2 * q2 + 1], acc);
-    }
-    emit(p, acc);
-  }
-}
-constexpr int LAPMAT_N = NPSQ * NPSQ;
-#endif
 
 __device__ __forceinline__ bool is_interior_pt(int p) { return p == 5 || p == 6 || p == 9 || p == 10; }
 
