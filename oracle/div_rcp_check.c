@@ -2,7 +2,9 @@
  * (hommexx_b200/csrc/hxx.cuh div_rcp): q = RN(x r), e = fma(-d, q, x), result = fma(e, r, q) with r = RN(1/d)
  * must equal the IEEE quotient RN(x / d) for every operand inside the kernels' exponent window. Operands are
  * drawn to hit the hard cases: random mantissas, mantissas next to a power of two, divisors with long runs
- * of ones, quotients next to a rounding boundary (x = q0 d +- a few ulps).
+ * of ones, quotients next to a representable value (x = q0 d +- a few ulps) and — the cases that decide correct
+ * rounding — quotients next to a TIE, the midpoint m = q0 + ulp(q0)/2 of two neighbouring doubles: x = RN(m d)
+ * formed in binary128 and perturbed by a few ulps, so that x / d lies within ~2^-53 ulp of the midpoint.
  *   div_rcp_check <millions of pairs> <seed>   ->  prints "<pairs> <mismatches>"                            */
 #include <math.h>
 #include <stdint.h>
@@ -49,7 +51,12 @@ int main(int argc, char** argv) {
     const int kind = (int)(rnd() & 63);
     double d = ldexp(mant(kind), (int)(rnd() % 80) - 40);           /* divisors: 2^-40 .. 2^40 */
     double x;
-    if (kind & 8) { /* a quotient next to a rounding boundary: x = q0 * d perturbed by a few ulps */
+    if ((kind & 24) == 24) { /* a quotient next to a tie: x ~ (q0 + ulp/2) d */
+      const double q0 = ldexp(mant(kind >> 3), (int)(rnd() % 60) - 30);
+      const __float128 m = (__float128)q0 + (__float128)(nextafter(q0, INFINITY) - q0) / 2;
+      x = (double)(m * (__float128)d);
+      x = from_bits(to_bits(x) + (rnd() % 5) - 2);
+    } else if (kind & 8) { /* a quotient next to a representable value: x = q0 * d perturbed by a few ulps */
       const double q0 = ldexp(mant(kind >> 3), (int)(rnd() % 60) - 30);
       x = q0 * d;
       x = from_bits(to_bits(x) + (rnd() % 5) - 2);
