@@ -132,16 +132,16 @@ def workload(args, n_gpus):
     return homme.preset("ne30", **over)
 
 
+def euler_advect_stage_bytes(nelem, qsize):
+    """Algorithmic HBM bytes of one euler_advect launch of each of the 3 stages of a tracer step (DESIGN.md section
+    4): per tracer read qdp + write qdp (+ read qtens_biharmonic on the hyperviscosity stage) + 2 qlim rows; per
+    element read derived_dp, divdp_proj, divdp, vn0 (2) (+ dpdiss_biharmonic on stage 3) and read+write the DSS
+    variable. Stage 2 also does that stage's min/max pass but reads the tracers once: the same bytes as stage 1."""
+    return [nelem * ((2 + hv) * qsize * F_BYTES + qsize * 2 * 72 * 8 + (5 + hv + 2) * F_BYTES) for hv in (0, 0, 1)]
+
+
 def euler_advect_bytes(nelem, qsize):
-    """Algorithmic HBM bytes of one euler_advect launch, averaged over the 3 stages of a tracer
-    step: per tracer read qdp + write qdp (+ read qtens_biharmonic on the
-    hyperviscosity stage) + 2 qlim rows; per element read derived_dp, divdp_proj, divdp, vn0 (2)
-    (+ dpdiss_biharmonic on stage 3) and read+write the DSS variable."""
-    per_stage = []
-    for hv in (0, 0, 1):
-        per_elem = (2 + hv) * qsize * F_BYTES + qsize * 2 * 72 * 8 + (5 + hv + 2) * F_BYTES
-        per_stage.append(per_elem)
-    return nelem * sum(per_stage) / 3.0
+    return sum(euler_advect_stage_bytes(nelem, qsize)) / 3.0
 
 
 def step_bytes_per_elem_step(cfg):
@@ -335,12 +335,13 @@ def main():
         torch.cuda.synchronize()
 
     kid = lib.hommexx_b200_kernel_id(b"euler_advect")
+    kids = [kid, lib.hommexx_b200_kernel_id(b"euler_advect_mm"), lib.hommexx_b200_kernel_id(b"euler_advect_hv")]
     for _ in range(args.warmup):
         h.run_subcycle()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    lib.hommexx_b200_profile(1 << kid)           # CUDA-event pair around every launch of the dominant kernel
+    lib.hommexx_b200_profile(sum(1 << k for k in kids))   # CUDA-event pair around every launch of the dominant kernel
     l0 = lib.hommexx_b200_launch_count()
     barrier()
     lib.hommexx_b200_event_record(0)
@@ -352,7 +353,13 @@ def main():
     launches = lib.hommexx_b200_launch_count() - l0
     clocks = sampler.stop()
     nl = C.c_int64()
-    k_ms = lib.hommexx_b200_profile_read(kid, C.byref(nl))
+    stage_ms, stage_n = [], []
+    for k in kids:   # the three stages of a tracer step are three variants of the kernel
+        n_ = C.c_int64()
+        stage_ms.append(lib.hommexx_b200_profile_read(k, C.byref(n_)))
+        stage_n.append(n_.value)
+    k_ms = sum(stage_ms)
+    nl.value = sum(stage_n)
     lib.hommexx_b200_profile(0)
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -372,7 +379,15 @@ def main():
         prof = json.loads(tf.read_text())
         traffic = prof.get("euler_advect_dram_bytes_per_launch")
         fp64_pct = prof.get("euler_advect_fp64_pipe_pct")
+    sb = euler_advect_stage_bytes(h.nelemd, cfg.qsize)
+    per_stage = {}
+    for name, b_, ms_, n_ in zip(("stage1 <HV=0,TAVG=0,MM=0>", "stage2 <0,0,1> (+ the stage's min/max pass)",
+                                  "stage3 <1,1,0> (hyperviscosity + time average)"), sb, stage_ms, stage_n):
+        if n_:
+            gbs = b_ / (ms_ / n_ * 1e-3) / 1e9
+            per_stage[name] = {"avg_launch_ms": ms_ / n_, "achieved": gbs, "frac": gbs / peak, "launches": n_}
     roofline = {"bound": "hbm", "kernel": "euler_advect_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "per_stage": per_stage,
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": adv_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": nl.value,
                 "kernel_share_of_step": k_ms / ms if ms > 0 else None,

@@ -541,13 +541,16 @@ void euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int d
   double* fdss = a.f_dss;
   const bool separate = (fdss == S.divdp_proj && a.rhsmdt != 0.0);
   if (separate) a.f_dss = nullptr;
-  PROBE(K_EULER_ADVECT);
+  // probe classes: euler_advect = the plain stage, euler_advect_mm = the stage that also does its min/max pass,
+  // euler_advect_hv = the hyperviscosity stage (they move different bytes per launch; bench.py rooflines each)
+  const int kid = hv ? K_EULER_ADVECT_HV : fuse_mm ? K_EULER_ADVECT_MM : K_EULER_ADVECT;
+  PROBE(kid);
   if (hv && tavg) euler_advect_kernel<true, true><<<adv_blocks, ADV_T, smem, S.stream>>>(a);
   else if (hv) euler_advect_kernel<true, false><<<adv_blocks, ADV_T, smem, S.stream>>>(a);
   else if (tavg) euler_advect_kernel<false, true><<<adv_blocks, ADV_T, smem, S.stream>>>(a);
   else if (fuse_mm) euler_advect_kernel<false, false, true><<<adv_blocks, ADV_T, smem, S.stream>>>(a);
   else euler_advect_kernel<false, false><<<adv_blocks, ADV_T, smem, S.stream>>>(a);
-  KERNEL_LAUNCHED(K_EULER_ADVECT);
+  KERNEL_LAUNCHED(kid);
   if (separate) {
     PROBE(K_EULER_FDSS);
     euler_fdss_kernel<<<S.nelemd, 288, 0, S.stream>>>(fdss, S.geo);

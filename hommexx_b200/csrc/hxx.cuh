@@ -66,7 +66,7 @@ constexpr int EPB = (NLEV * 4 <= 288) ? 4 : 2;
 enum KernelId {
   K_CAAR = 0, K_DSS, K_HALO_PACK, K_RK_COMBINE, K_DP3D_FROM_PS, K_STEP_INIT, K_HV_FIRST, K_HV_SECOND, K_HV_UPDATE,
   K_EULER_DIVDP, K_EULER_QMINMAX, K_MINMAX, K_EULER_ADVECT, K_EULER_FDSS, K_EULER_TAVG, K_REMAP, K_UPDATE_Q,
-  K_TRANSPOSE, K_HOOK, K_FORCING, K_DIAG, K_COUNT
+  K_TRANSPOSE, K_HOOK, K_FORCING, K_DIAG, K_EULER_ADVECT_MM, K_EULER_ADVECT_HV, K_COUNT
 };
 extern const char* const kernel_names[K_COUNT];
 

@@ -34,7 +34,7 @@ const char* const kernel_names[K_COUNT] = {
     "caar", "dss", "halo_pack", "rk_combine", "dp3d_from_ps", "prim_step_init", "hv_first_laplace",
     "hv_second_laplace_pre_exchange", "hv_update_states", "euler_divdp", "euler_qminmax", "minmax",
     "euler_advect", "euler_fdss", "euler_time_avg", "remap", "update_q", "transpose", "hook", "cam_forcing",
-    "diagnostics"};
+    "diagnostics", "euler_advect_mm", "euler_advect_hv"};
 
 // ---- per-kernel CUDA-event probes (on the launch stream) -----------------------------------
 namespace {
