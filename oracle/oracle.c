@@ -10,15 +10,16 @@
  * accumulators starting from 0), compiled with -ffp-contract=off so no FMA contraction
  * changes the rounding. File:line citations are relative to /root/reference/src/share/cxx/.
  *
- * Parity pins (tests/test_oracle_*.py): the reference's known-answer vectors
- * test/unit_tests/inputs/{gradient,divergence,vorticity}_sphere_np4.in; bitwise agreement
- * of the PPM remap with the reference's own plain-C++ twin src/preqx/unit_tests/remap.cpp
- * compiled into oracle/_ref/; the limiter property tests of preqx_ut.cpp:1335-1531.
- * CAM forcing and diagnostics are checked against a direct numpy restatement of the reference
- * formulas (tests/test_oracle_forcing_diag.py); the rsplit = 0 path against the vertically Lagrangian
- * one (tests/test_oracle_rsplit0.py: same equations, different discretisation, truncation-error agreement).
- * There is no stored whole-timestep output in the reference, so whole-step parity of the
- * CUDA path is oracle-vs-CUDA.
+ * PINNED TO THE REFERENCE'S OWN BUILD (tests/test_oracle_vs_reference.py): oracle/_ref/libref_hommexx_*.so is the
+ * reference's src/share/cxx compiled from its sources (oracle/Makefile ref_full, against the serial Kokkos stand-in of
+ * oracle/ref_shim, VECTOR_SIZE 1, -ffp-contract=off); this file is bit-identical to it on v, T, dp3d, ps_v, Qdp, Q,
+ * omega_p after 10-12 dynamics steps in 11 configurations (every option variant, 40 distinct tracers), in three
+ * forced runs and on the diagnostics accumulators. Earlier pins, still run: the reference's known-answer vectors
+ * test/unit_tests/inputs/{gradient,divergence,vorticity}_sphere_np4.in; bitwise agreement of the PPM remap with the
+ * reference's plain-C++ twin src/preqx/unit_tests/remap.cpp; the limiter property tests of preqx_ut.cpp:1335-1531;
+ * CAM forcing and diagnostics against a numpy restatement of the reference formulas; the rsplit = 0 path against
+ * the vertically Lagrangian one. What this file adds over the reference build are the phase-level hooks of section C
+ * of the ABI (the reference exposes its functors only as C++ classes), which the per-phase CUDA tests need.
  */
 #include <math.h>
 #include <stdbool.h>
