@@ -58,9 +58,14 @@ struct ColData {
 // warp. On entry c.dpo[PAD..] holds the source thickness and c.tgt the target thickness.
 // Returns false when the target grid is not monotone (kid would leave the column): the reference
 // has undefined behaviour there; here the index is clamped and the caller raises the abort flag.
+// `displaced` is set when a target level lies more than MAX_LAG levels below the source cell that holds its
+// lower interface: the in-place sweep of the production kernel stores a chunk only after the chunk of the same
+// levels has been staged, which such a displacement (a Lagrangian surface crossing five reference layers in one
+// remap interval) would break — the run aborts with its own message instead of overwriting values not yet read.
+constexpr int MAX_LAG = CH + 1;
 // `scratch` holds the two interface arrays pio[NLEV+2], pin[NLEV+1] (only needed here).
-__device__ bool ppm_column_grids(ColData& c, double* scratch, int lane) {
-  bool ok = true;
+__device__ bool ppm_column_grids(ColData& c, double* scratch, int lane, bool* displaced = nullptr) {
+  bool ok = true, lag = false;
   double* const pio = scratch;
   double* const pin = scratch + NLEV + 2;
   if (lane < 2) {
@@ -95,6 +100,7 @@ __device__ bool ppm_column_grids(ColData& c, double* scratch, int lane) {
     kk--;
     if (kk == NLEV + 1) kk = NLEV;
     if (kk < 1) { kk = 1; ok = false; }
+    lag |= (k - (kk - 1) > MAX_LAG);
     c.kid[k] = kk - 1;
     const double z2 = (pin[k + 1] - (pio[kk - 1] + pio[kk]) * 0.5) / c.dpo[kk + 1 + PAD - 2];
     // integrate_parabola :668-673 with x1 = -0.5: x1*x1 = 0.25 and x1*x1*x1 = -0.125 exactly
@@ -121,6 +127,8 @@ __device__ bool ppm_column_grids(ColData& c, double* scratch, int lane) {
     c.p9[j] = dx[j + 2] * (dx[j + 2] + dx[j + 3]) / (dx[j + 1] + 2.0 * dx[j + 2]);
   }
   __syncwarp();
+  lag = __any_sync(0xffffffffu, lag);
+  if (displaced) *displaced = lag;
   return !__any_sync(0xffffffffu, !ok);
 }
 
@@ -287,7 +295,9 @@ __global__ void __launch_bounds__(REMAP_MAX_WARPS * 32) remap_kernel(const Remap
     // compute_target_thickness :417-437
     for (int k = lane; k < NLEV; k += 32) c.tgt[k] = dc.dai[k] * dc.ps0 + dc.dbi[k] * ps;
     __syncwarp();
-    if (!ppm_column_grids(c, stage_all + (size_t)w * STAGE_PER_WARP, lane) && lane == 0) atomicOr(a.invalid, 1);
+    bool displaced = false;
+    if (!ppm_column_grids(c, stage_all + (size_t)w * STAGE_PER_WARP, lane, &displaced) && lane == 0) atomicOr(a.invalid, 1);
+    if (displaced && lane == 0) { atomicOr(a.invalid, 2); c.ok = 0; }
   }
   __syncthreads();
 
@@ -453,7 +463,10 @@ void check_remap_flag() {
   if (!S.invalid_flag) return;
   CUDA_OK(cudaMemcpyAsync(S.h_invalid, S.invalid_flag, sizeof(int), cudaMemcpyDeviceToHost, S.stream));
   CUDA_OK(cudaStreamSynchronize(S.stream));
-  if (*S.h_invalid) runtime_abort("Negative (or nan) layer thickness detected, aborting!", 101);
+  if (*S.h_invalid & 1) runtime_abort("Negative (or nan) layer thickness detected, aborting!", 101);
+  if (*S.h_invalid & 2)
+    runtime_abort("vertical remap: a Lagrangian level moved more than five reference layers in one remap interval "
+                  "(unsupported by the in-place sweep), aborting!", 101);
 }
 
 // ---- test hook: remap_Q_ppm semantics on caller-provided columns ---------------------------
