@@ -3,8 +3,120 @@
 // reference's own src/share/cxx sources compiled against the serial Kokkos stand-in of oracle/ref_shim — binds to the
 // same driver as the product and the oracle. Everything in section A comes from the reference's own
 // cxx_f90_interface.cpp / prim_driver.cpp / mpi_cxx_f90_interface.cpp. TEST INFRASTRUCTURE.
+//
+// Section C (phase-level hooks) is bound to the public run methods of the reference's functors, so that the oracle
+// can be pinned PER FUNCTOR as well as per run: hxx_caar_run -> CaarFunctor::run, hxx_hypervis_run ->
+// HyperviscosityFunctor::run, hxx_euler_* -> EulerStepFunctor::{reset,precompute_divdp,euler_step,qdp_time_avg},
+// hxx_vertical_remap -> VerticalRemapManager::run_remap, hxx_update_q -> update_q (prim_driver.cpp); and
+// hxx_get_field / hxx_set_field copy the reference's Views out / in. With HOMMEXX_VECTOR_SIZE = 1 a View
+// Scalar*[..][NP][NP][NUM_LEV] is exactly the level-innermost [nelemd][..][np][np][nlev] layout of the ABI.
 #include <cstdint>
+#ifdef REF_API_PHASE_HOOKS  // the serial VECTOR_SIZE = 1 builds only
+#include <cstring>
+
+#include "CaarFunctor.hpp"
+#include "Context.hpp"
+#include "Elements.hpp"
+#include "EulerStepFunctor.hpp"
+#include "HyperviscosityFunctor.hpp"
+#include "SimulationParams.hpp"
+#include "TimeLevel.hpp"
+#include "Tracers.hpp"
+#include "VerticalRemapManager.hpp"
+
+namespace Homme {
+void update_q(const int np1_qdp, const int np1);
+}
+
+namespace {
+using namespace Homme;
+static_assert(sizeof(Scalar) == sizeof(double), "the field hooks need the scalar (VECTOR_SIZE = 1) build");
+
+struct Span {
+  double* p = nullptr;
+  size_t n = 0;
+};
+template <typename V>
+Span span_of(const V& v) {
+  return Span{reinterpret_cast<double*>(v.data()), static_cast<size_t>(v.size())};
+}
+
+Span ref_field(const char* name) {
+  Elements& e = Context::singleton().get_elements();
+  Tracers& t = Context::singleton().get_tracers();
+  auto is = [&](const char* s) { return std::strcmp(name, s) == 0; };
+  if (is("v")) return span_of(e.m_v);
+  if (is("t")) return span_of(e.m_t);
+  if (is("dp3d")) return span_of(e.m_dp3d);
+  if (is("ps_v")) return span_of(e.m_ps_v);
+  if (is("phi")) return span_of(e.m_phi);
+  if (is("omega_p")) return span_of(e.m_omega_p);
+  if (is("eta_dot_dpdn")) return span_of(e.m_eta_dot_dpdn);
+  if (is("derived_vn0")) return span_of(e.m_derived_vn0);
+  if (is("derived_dp")) return span_of(e.m_derived_dp);
+  if (is("divdp")) return span_of(e.m_derived_divdp);
+  if (is("divdp_proj")) return span_of(e.m_derived_divdp_proj);
+  if (is("dpdiss_ave")) return span_of(e.m_derived_dpdiss_ave);
+  if (is("dpdiss_biharmonic")) return span_of(e.m_derived_dpdiss_biharmonic);
+  if (is("vtens")) return span_of(e.buffers.vtens);
+  if (is("ttens")) return span_of(e.buffers.ttens);
+  if (is("dptens")) return span_of(e.buffers.dptens);
+  if (is("vstar")) return span_of(e.buffers.vstar);
+  if (is("dpdissk")) return span_of(e.buffers.dpdissk);
+  if (is("fm")) return span_of(e.m_fm);
+  if (is("ft")) return span_of(e.m_ft);
+  if (is("qdp")) return span_of(t.qdp);
+  if (is("qtens_biharmonic")) return span_of(t.qtens_biharmonic);
+  if (is("qlim")) return span_of(t.qlim);
+  if (is("Q")) return span_of(t.Q);
+  if (is("fq")) return span_of(t.fq);
+  return Span{};
+}
+}  // namespace
+#endif
+
 extern "C" {
+#ifdef REF_API_PHASE_HOOKS
+int64_t hxx_get_field(const char* name, double* out) {
+  const Span s = ref_field(name);
+  if (s.p && out) std::memcpy(out, s.p, s.n * sizeof(double));
+  return static_cast<int64_t>(s.n);
+}
+int64_t hxx_set_field(const char* name, const double* in) {
+  const Span s = ref_field(name);
+  if (s.p && in) std::memcpy(s.p, in, s.n * sizeof(double));
+  return static_cast<int64_t>(s.n);
+}
+void hxx_caar_run(int nm1, int n0, int np1, double dt, double eta_ave_w, int n0_qdp, int with_dss) {
+  CaarFunctor& f = Context::singleton().get_caar_functor();
+  f.set_n0_qdp(n0_qdp);
+  if (with_dss) {
+    f.run(nm1, n0, np1, dt, eta_ave_w, false);
+  } else {
+    f.set_rk_stage_data(nm1, n0, np1, dt, eta_ave_w, false);
+    f.run();
+  }
+}
+void hxx_hypervis_run(int np1, double dt, double eta_ave_w) {
+  Context::singleton().get_hyperviscosity_functor().run(np1, dt, eta_ave_w);
+}
+void hxx_euler_reset(void) {
+  Context::singleton().get_euler_step_functor().reset(Context::singleton().get_simulation_params());
+}
+void hxx_euler_precompute_divdp(void) { Context::singleton().get_euler_step_functor().precompute_divdp(); }
+void hxx_euler_step(int np1_qdp, int n0_qdp, double dt, double rhs_multiplier, int dss_opt) {
+  const DSSOption opt = dss_opt == 0 ? DSSOption::ETA : dss_opt == 1 ? DSSOption::OMEGA : DSSOption::DIV_VDP_AVE;
+  Context::singleton().get_euler_step_functor().euler_step(np1_qdp, n0_qdp, dt, rhs_multiplier, opt);
+}
+void hxx_euler_qdp_time_avg(int n0_qdp, int np1_qdp) {
+  Context::singleton().get_euler_step_functor().qdp_time_avg(n0_qdp, np1_qdp);
+}
+void hxx_vertical_remap(int np1, int np1_qdp, double dt) {
+  Context::singleton().get_vertical_remap_manager().run_remap(np1, np1_qdp, dt);
+}
+void hxx_update_q(int np1_qdp, int np1) { Homme::update_q(np1_qdp, np1); }
+#endif
+
 int hommexx_b200_nlev(void) { return PLEV; }
 int hommexx_b200_qsize_d(void) { return QSIZE_D; }
 const char* hommexx_b200_backend(void) { return "reference-serial"; }
