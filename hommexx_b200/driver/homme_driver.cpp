@@ -834,6 +834,12 @@ void hd_time_levels(const HommeDriver* h, int* nstep, int* nm1, int* n0, int* np
   *nstep = h->nstep; *nm1 = h->nm1; *n0 = h->n0; *np1 = h->np1;
 }
 
+// restart runs (runtype = 1): the time levels ReadRestart (restart_io_mod.F90:669-698) restores with elem%state;
+// call before hd_init_dycore / hd_upload_state, which hand them to init_time_level_c. 1-based like hd_time_levels.
+void hd_set_time_levels(HommeDriver* h, int nstep, int nm1, int n0, int np1) {
+  h->nstep = nstep; h->nm1 = nm1; h->n0 = n0; h->np1 = np1;
+}
+
 const int* hd_local_gids(const HommeDriver* h) { return h->local_gids.data(); }
 const int* hd_owner(const HommeDriver* h) { return h->owner.data(); }
 

@@ -156,6 +156,8 @@ def driver_lib() -> C.CDLL:
         d.hd_array.restype = C.POINTER(C.c_double)
         d.hd_connections.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int))]
         d.hd_time_levels.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        d.hd_set_time_levels.argtypes = [C.c_void_p] + [C.c_int] * 4
+        d.hd_set_time_levels.restype = None
         d.hd_local_gids.argtypes = [C.c_void_p]
         d.hd_local_gids.restype = C.POINTER(C.c_int)
         d.hd_owner.argtypes = [C.c_void_p]
@@ -310,6 +312,30 @@ class Homme:
         v = [C.c_int() for _ in range(4)]
         self.d.hd_time_levels(self.h, *[C.byref(x) for x in v])
         return tuple(x.value for x in v)  # nstep, nm1, n0, np1 (1-based levels)
+
+    # -- restart (WriteRestart / ReadRestart of restart_io_mod.F90:626-698: elem%state and the time levels) ---------
+    RESTART_ARRAYS = ("v", "T", "dp3d", "ps_v", "Qdp", "Q")
+
+    def write_restart(self, path):
+        """Pull the state (cxx_push_results_to_f90) and write it with the time levels; one file per rank."""
+        self.push_results()
+        c = self.cfg
+        np.savez(path, tl=np.array(self.time_levels(), dtype=np.int64), gids=self.local_gids(),
+                 dims=np.array([c.ne, c.nlev, c.qsize, c.qsize_d], dtype=np.int64),
+                 **{k: self.array(k) for k in self.RESTART_ARRAYS})
+
+    def read_restart(self, path):
+        """Restore the driver's arrays and time levels from write_restart; call BEFORE init_dycore (a restart run
+        initialises the dycore from the restored elem%state, prim_main.F90:181-262) or follow it with upload_state()."""
+        c = self.cfg
+        with np.load(path) as z:
+            if tuple(z["dims"]) != (c.ne, c.nlev, c.qsize, c.qsize_d):
+                raise ValueError(f"{path}: written for (ne, nlev, qsize, qsize_d) = {tuple(z['dims'])}")
+            if not np.array_equal(z["gids"], self.local_gids()):
+                raise ValueError(f"{path}: written for a different partition (rank's element list differs)")
+            for k in self.RESTART_ARRAYS:
+                self.array(k)[:] = z[k]
+            self.d.hd_set_time_levels(self.h, *[int(x) for x in z["tl"]])
 
     def local_gids(self) -> np.ndarray:
         return np.ctypeslib.as_array(self.d.hd_local_gids(self.h), shape=(self.nelemd,)).copy()

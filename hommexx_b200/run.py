@@ -1,6 +1,6 @@
 """Namelist-driven run of the preqx dycore: the stand-in for `prim_main` on this side of the C ABI.
 
-    python -m hommexx_b200.run hommexx_b200/namelists/prtcA-r3-dry.nl [--lib cuda|oracle] [--nmax N] [--held-suarez]
+    python -m hommexx_b200.run hommexx_b200/namelists/prtcA-r3-dry.nl [--nmax N] [--held-suarez]
 
 Reads a HOMME `ctl_nl` / `vert_nl` namelist (the reference's own .nl files work: unknown keys are ignored),
 builds the mesh and the Jablonowski-Williamson state with the C++ driver, steps `prim_run_subcycle_c` until
@@ -8,7 +8,9 @@ builds the mesh and the Jablonowski-Williamson state with the C++ driver, steps 
 prints a `prim_printstate`-style block: min / max of the prognostic fields at the current time level and
 the global integrals of the `elem%accum` energies and tracer masses the dycore's diagnostics wrote
 (Diagnostics.cpp:37-185; global_integral = sum(spheremp * f) / (4 pi), prim_state_mod.F90).
-Host orchestration only; `--lib oracle` (TEST INFRASTRUCTURE, CPU) is for machines without a GPU.
+Restarts follow prim_main.F90:181-262,355: `restartfreq` > 0 (steps) writes `restartdir/R<nstep>.npz` (elem%state and
+the time levels, WriteRestart), `runtype = 1` with `restartfile` resumes from one; the resumed run is bit-identical
+to the uninterrupted one. Host orchestration only; the dycore is the CUDA library (no CPU fallback).
 """
 from __future__ import annotations
 
@@ -119,12 +121,15 @@ def printstate(h, out=sys.stdout):
     return res
 
 
-def run(cfg: homme.Config, libpath, nmax: int, held_suarez: bool = False, out=sys.stdout):
+def run(cfg: homme.Config, libpath, nmax: int, held_suarez: bool = False, out=sys.stdout, restart_in=None,
+        restartfreq: int = 0, restartdir: str = "."):
     h = homme.Homme(cfg, libpath)
     h.set_last_step(nmax)  # nEndStep: switches the last step's diagnostics on (prim_driver.cpp:55-57)
+    if restart_in:         # runtype = 1: elem%state and tl come from the file, then the usual initialisation
+        h.read_restart(restart_in)
     h.init_dycore()
     history = []
-    nstep = 0
+    nstep = h.time_levels()[0]
     while nstep < nmax:
         if held_suarez:
             from . import held_suarez as hs
@@ -134,6 +139,10 @@ def run(cfg: homme.Config, libpath, nmax: int, held_suarez: bool = False, out=sy
         if nstep % cfg.state_frequency == 0 or nstep >= nmax:  # prim_main.F90:312-321
             h.push_results()
             history.append(printstate(h, out))
+        if restartfreq > 0 and nstep % restartfreq == 0:                       # prim_main.F90:355
+            import os
+            os.makedirs(restartdir, exist_ok=True)
+            h.write_restart(os.path.join(restartdir, f"R{nstep:09d}.npz"))
     h.close()
     return history
 
@@ -146,9 +155,13 @@ def main(argv=None):
     args = ap.parse_args(argv)
     nl = parse_namelist(open(args.namelist).read())
     cfg = config_from_namelist(nl)
-    nmax = args.nmax or int(nl.get("ctl_nl", {}).get("nmax", 12))
+    ctl = nl.get("ctl_nl", {})
+    nmax = args.nmax or int(ctl.get("nmax", 12))
+    restart_in = str(ctl["restartfile"]) if int(ctl.get("runtype", 0)) == 1 else None
     # the product has one backend: the CUDA library (load_dycore raises if it is not built; no CPU fallback)
-    run(cfg, homme.cuda_lib_path(cfg.nlev, cfg.qsize_d), nmax, args.held_suarez)
+    run(cfg, homme.cuda_lib_path(cfg.nlev, cfg.qsize_d), nmax, args.held_suarez, restart_in=restart_in,
+        restartfreq=max(0, int(float(ctl.get("restartfreq", 0)) * 86400.0 / cfg.tstep)),  # days -> steps, namelist_mod.F90:482
+        restartdir=str(ctl.get("restartdir", "./restart")))
 
 
 if __name__ == "__main__":
