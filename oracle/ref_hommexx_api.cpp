@@ -13,13 +13,17 @@
 #include <cstdint>
 #ifdef REF_API_PHASE_HOOKS  // the serial VECTOR_SIZE = 1 builds only
 #include <cstring>
+#include <string>
 
 #include "CaarFunctor.hpp"
 #include "Context.hpp"
 #include "Elements.hpp"
 #include "EulerStepFunctor.hpp"
 #include "HyperviscosityFunctor.hpp"
+#include "Derivative.hpp"
+#include "KernelVariables.hpp"
 #include "SimulationParams.hpp"
+#include "SphereOperators.hpp"
 #include "TimeLevel.hpp"
 #include "Tracers.hpp"
 #include "VerticalRemapManager.hpp"
@@ -115,6 +119,32 @@ void hxx_vertical_remap(int np1, int np1_qdp, double dt) {
   Context::singleton().get_vertical_remap_manager().run_remap(np1, np1_qdp, dt);
 }
 void hxx_update_q(int np1_qdp, int np1) { Homme::update_q(np1_qdp, np1); }
+// One element-local operator of SphereOperators.hpp on caller-provided [np][np][nlev] fields of element `ie`
+// (a team per element as in the functors; only the team of `ie` works). Returns silently on an unknown name.
+void hxx_sphere_op(const char* op, int ie, const double* in, double* out, double nu_ratio) {
+  Elements& e = Context::singleton().get_elements();
+  SphereOperators sph(e, Context::singleton().get_derivative());
+  const auto policy = Homme::get_default_team_policy<ExecSpace>(e.num_elems());
+  sph.allocate_buffers(policy);
+  ExecViewManaged<Scalar[2][NP][NP][NUM_LEV]> vin("sphere_op in"), vout("sphere_op out");
+  const size_t F = NP * NP * NUM_LEV;
+  const std::string name(op);
+  const int n_in = (name == "gradient_sphere" || name == "laplace_simple") ? 1 : 2;
+  const int n_out = (name == "gradient_sphere" || name == "vlaplace_sphere_wk_contra") ? 2 : 1;
+  std::memcpy(vin.data(), in, n_in * F * sizeof(double));
+  Kokkos::parallel_for(policy, KOKKOS_LAMBDA(const TeamMember& team) {
+    KernelVariables kv(team);
+    if (kv.ie != ie) return;
+    if (name == "gradient_sphere") sph.gradient_sphere(kv, Homme::subview(vin, 0), vout);
+    else if (name == "divergence_sphere") sph.divergence_sphere(kv, vin, Homme::subview(vout, 0));
+    else if (name == "vorticity_sphere")
+      sph.vorticity_sphere(kv, Homme::subview(vin, 0), Homme::subview(vin, 1), Homme::subview(vout, 0));
+    else if (name == "laplace_simple") sph.laplace_simple(kv, Homme::subview(vin, 0), Homme::subview(vout, 0));
+    else if (name == "divergence_sphere_wk") sph.divergence_sphere_wk(kv, vin, Homme::subview(vout, 0));
+    else if (name == "vlaplace_sphere_wk_contra") sph.vlaplace_sphere_wk_contra(kv, nu_ratio, vin, vout);
+  });
+  std::memcpy(out, vout.data(), n_out * F * sizeof(double));
+}
 #endif
 
 int hommexx_b200_nlev(void) { return PLEV; }
