@@ -19,6 +19,7 @@
 #include "Context.hpp"
 #include "Elements.hpp"
 #include "EulerStepFunctor.hpp"
+#include "EulerStepFunctorImpl.hpp"
 #include "HyperviscosityFunctor.hpp"
 #include "Derivative.hpp"
 #include "KernelVariables.hpp"
@@ -144,6 +145,32 @@ void hxx_sphere_op(const char* op, int ie, const double* in, double* out, double
     else if (name == "vlaplace_sphere_wk_contra") sph.vlaplace_sphere_wk_contra(kv, nu_ratio, vin, vout);
   });
   std::memcpy(out, vout.data(), n_out * F * sizeof(double));
+}
+// The limiters of EulerStepFunctorImpl.hpp on nsets independent problems [set][np*np][nlev], qlim [set][2][nlev]:
+// limiter_option 8 / 9 = what limiter_optim_iter_full(kv) / limiter_clip_and_sum(kv) dispatch to on a host
+// execution space (SerialLimiter::run<8|9>, :640-666); 108 / 109 = the team implementations the reference's unit
+// tests and its GPU build call (:766-884).
+void hxx_limiter(int limiter_option, int nsets, const double* sphweights, const double* dpmass, double* ptens,
+                 double* qlim) {
+  const size_t F = NP * NP * NUM_LEV;
+  ExecViewManaged<Real[NP][NP]> sw("sphweights");
+  ExecViewManaged<Scalar[NP][NP][NUM_LEV]> dm("dpmass"), pt("ptens"), wrk("rwrk");
+  ExecViewManaged<Scalar[2][NUM_LEV]> ql("qlim");
+  const auto policy = Kokkos::TeamPolicy<ExecSpace>(1, 1, 1);
+  for (int s = 0; s < nsets; ++s) {
+    std::memcpy(sw.data(), sphweights + (size_t)s * NP * NP, NP * NP * sizeof(double));
+    std::memcpy(dm.data(), dpmass + s * F, F * sizeof(double));
+    std::memcpy(pt.data(), ptens + s * F, F * sizeof(double));
+    std::memcpy(ql.data(), qlim + (size_t)s * 2 * NUM_LEV, 2 * NUM_LEV * sizeof(double));
+    Kokkos::parallel_for(policy, KOKKOS_LAMBDA(const TeamMember& team) {
+      if (limiter_option == 8) SerialLimiter<ExecSpace>::run<8>(sw, dm, ql, pt, wrk);
+      else if (limiter_option == 9) SerialLimiter<ExecSpace>::run<9>(sw, dm, ql, pt, wrk);
+      else if (limiter_option == 108) EulerStepFunctorImpl::limiter_optim_iter_full(team, sw, dm, ql, pt);
+      else if (limiter_option == 109) EulerStepFunctorImpl::limiter_clip_and_sum(team, sw, dm, ql, pt);
+    });
+    std::memcpy(ptens + s * F, pt.data(), F * sizeof(double));
+    std::memcpy(qlim + (size_t)s * 2 * NUM_LEV, ql.data(), 2 * NUM_LEV * sizeof(double));
+  }
 }
 #endif
 
