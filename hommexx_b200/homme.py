@@ -176,7 +176,7 @@ def load_dycore(path) -> C.CDLL:
     lib.hommexx_b200_launch_count.restype = C.c_int64
     lib.hommexx_b200_set_comm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
     # section C (phase-level hooks): every product / oracle library has them; the reference's own build under
-    # oracle/_ref exports sections A and B only
+    # oracle/_ref binds the functor-level ones to the reference's objects (oracle/ref_hommexx_api.cpp)
     sigs = {
         "hxx_caar_run": ([C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int], None),
         "hxx_rk_combine": ([C.c_int, C.c_int], None),
