@@ -9,7 +9,7 @@ module hommexx_b200_mod
   use iso_c_binding, only: c_int, c_char, c_int64_t, c_double, c_ptr
   implicit none
   private
-  public :: hommexx_b200_wire_gpus
+  public :: hommexx_b200_wire_gpus, hxx_held_suarez_forcing
 
   interface
     ! int hommexx_b200_nccl_unique_id(void* out128)
@@ -29,6 +29,14 @@ module hommexx_b200_mod
       import :: c_int64_t
       integer(kind=c_int64_t) :: n
     end function
+    ! void hxx_held_suarez_forcing(const double* lat, const double* hyam, const double* hybm)   (section C)
+    ! Held-Suarez FM / FT evaluated on the device from the dycore's own state at n0, in place of hs_forcing +
+    ! f90_push_forcing_to_cxx: call before prim_run_subcycle_c with ftype = 0. lat = elem(:)%spherep(:,:)%lat packed
+    ! [np, np, nelemd] (read on the first call only), hyam / hybm = hvcoord%hyam, hvcoord%hybm.
+    subroutine hxx_held_suarez_forcing(lat, hyam, hybm) bind(c, name="hxx_held_suarez_forcing")
+      import :: c_double
+      real(kind=c_double), intent(in) :: lat(*), hyam(*), hybm(*)
+    end subroutine
   end interface
 
 contains
