@@ -35,13 +35,18 @@ constexpr int REMAP_UNROLL = HXX_REMAP_UNROLL;
 constexpr int PAD = 2;
 constexpr int RC = 4;        // columns per block
 constexpr int CH = 4;        // levels per staged chunk (32 B per column-field)
-constexpr int RS = CH + 1;   // staging row stride in doubles (odd: conflict-free)
+constexpr int RS = CH;       // staging row stride in doubles; the level slot inside a row is rotated by the row's
+                             // index / 4 (stage_slot), so 16 lanes reading their own rows hit 16 different banks
 constexpr int NBUF = 2;      // input chunks in flight per warp
 constexpr int NCHUNK = (NLEV + CH - 1) / CH;
-// per-warp staging: NBUF input chunks, the output chunk and its Q twin ([32 rows][RS] each), and
-// the two per-row pointer tables (field, Q); the input rows double as phase-1 scratch
-constexpr int STAGE_PER_WARP = (NBUF + 2) * 32 * RS + 64;
+// per-warp staging: NBUF input chunks and the output chunk ([32 rows][RS] each), and the two per-row pointer
+// tables (field, Q); the input rows double as phase-1 scratch. Shared memory is what bounds the occupancy of the
+// production kernel: 4 columns of ColData + 6 warps of staging = 56.9 KB per block at (72, 40), four blocks per SM.
+constexpr int STAGE_PER_WARP = (NBUF + 1) * 32 * RS + 64;
 static_assert(STAGE_PER_WARP >= 2 * NLEV + 3, "phase-1 scratch does not fit the staging rows");
+static_assert(CH == 4 && NLEV <= 255, "stage_slot and the byte-sized kid assume 4-level chunks and < 256 levels");
+// slot of (row, level) inside a [32][RS] staging buffer
+__device__ __forceinline__ int stage_slot(int row, int level) { return row * RS + ((level + (row >> 2)) & (CH - 1)); }
 
 struct ColData {
   double p0[NLEV + 2], p1[NLEV + 2], p2[NLEV + 2];                               // ppmdx 0..2, j = 0..NLEV+1
@@ -49,10 +54,11 @@ struct ColData {
   double dpo[NLEV + 4], rdpo[NLEV];
   double tgt[NLEV], rtgt[NLEV];
   double d1[NLEV], d2[NLEV], d3[NLEV];  // x2-x1, x2^2-x1^2, x2^3-x1^3 of integrate_parabola, x1 = -1/2, x2 = z2
-  int kid[NLEV];
+  unsigned char kid[NLEV];
   int ok;
   int pad_;
 };
+static_assert(sizeof(ColData) % 8 == 0, "ColData is laid out as an array of doubles");
 
 // compute_partitions :506-597 + compute_integral_bounds :600-666 + compute_grids :366-413, by one
 // warp. On entry c.dpo[PAD..] holds the source thickness and c.tgt the target thickness.
@@ -101,7 +107,7 @@ __device__ bool ppm_column_grids(ColData& c, double* scratch, int lane, bool* di
     if (kk == NLEV + 1) kk = NLEV;
     if (kk < 1) { kk = 1; ok = false; }
     lag |= (k - (kk - 1) > MAX_LAG);
-    c.kid[k] = kk - 1;
+    c.kid[k] = (unsigned char)(kk - 1);
     const double z2 = (pin[k + 1] - (pio[kk - 1] + pio[kk]) * 0.5) / c.dpo[kk + 1 + PAD - 2];
     // integrate_parabola :668-673 with x1 = -0.5: x1*x1 = 0.25 and x1*x1*x1 = -0.125 exactly
     c.d1[k] = z2 - (-0.5);
@@ -150,7 +156,8 @@ __device__ __forceinline__ double ppm_ai(double a0, double a1, double dma_j1, do
 // One (column, field) sweep of compute_remap_phase :203-266, top-down, PPM stencil in registers.
 //   tick(ln)      called by every lane (active or not) before level ln (2 <= ln < NLEV) is read
 //   load(k)       raw field value at level k; multiplied by the source thickness when `state`
-//   emit(k, x, t) remapped mass x of target level k (increasing k) and t = x / target thickness
+//   emit(k, x)    remapped mass x of target level k (increasing k); x / target thickness (the value a state leaves
+//                 with, and Q of a tracer) is div_rcp(x, c.tgt[k], c.rtgt[k]), left to the caller
 template <class Tick, class Load, class Emit>
 __device__ __forceinline__ void ppm_sweep(const ColData& c, int alg, bool active, bool state, Tick tick, Load load,
                                           Emit emit) {
@@ -187,7 +194,7 @@ __device__ __forceinline__ void ppm_sweep(const ColData& c, int alg, bool active
       const double massn = Mc + integral * dpo_c;
       const double out = kt > 0 ? massn - massn_prev : massn;
       massn_prev = massn;
-      emit(kt, out, div_rcp(out, c.tgt[kt], c.rtgt[kt]));
+      emit(kt, out);
       ++kt;
       kid_next = kt < NLEV ? c.kid[kt] : -1;
     }
@@ -332,8 +339,7 @@ __global__ void __launch_bounds__(REMAP_MAX_WARPS * 32) remap_kernel(const Remap
   const bool state = f < 3;
   double* const stage = stage_all + (size_t)w * STAGE_PER_WARP;
   double* const obuf = stage + NBUF * 32 * RS;
-  double* const qbuf = obuf + 32 * RS;
-  double** const ptab = reinterpret_cast<double**>(qbuf + 32 * RS);  // row -> field column
+  double** const ptab = reinterpret_cast<double**>(obuf + 32 * RS);  // row -> field column
   double** const qtab = ptab + 32;                                   // row -> Q column (null for states)
   __syncwarp();
   ptab[lane] = field_ptr(f < m.nf ? f : 0);
@@ -346,14 +352,14 @@ __global__ void __launch_bounds__(REMAP_MAX_WARPS * 32) remap_kernel(const Remap
 #pragma unroll
       for (int i = 0; i < CH; ++i) {
         const int e = i * 32 + lane, row = e / CH, lev = e % CH, level = chunk * CH + lev;
-        if (((amask >> row) & 1u) && level < NLEV) cp_async8(dstb + row * RS + lev, ptab[row] + level);
+        if (((amask >> row) & 1u) && level < NLEV) cp_async8(dstb + stage_slot(row, lev), ptab[row] + level);
       }
     }
     cp_async_commit();
   };
   prefetch(0);
   // staged raw value of this lane's field at `level` (chunk must have landed)
-  auto staged = [&](int level) { return stage[((level / CH) % NBUF) * 32 * RS + lane * RS + level % CH]; };
+  auto staged = [&](int level) { return stage[((level / CH) % NBUF) * 32 * RS + stage_slot(lane, level)]; };
   ppm_sweep(
       c, a.alg, active, state,
       [&](int ln) {  // uniform per step: before level ln is read
@@ -364,12 +370,12 @@ __global__ void __launch_bounds__(REMAP_MAX_WARPS * 32) remap_kernel(const Remap
         }
       },
       staged,
-      [&](int k, double out, double over_tgt) {
-        // states leave as x / tgt (ComputeIntrinsicsTag :294-307); tracers as Qdp = x and Q = x / tgt (update_q)
-        obuf[lane * RS + k % CH] = state ? over_tgt : out;
-        qbuf[lane * RS + k % CH] = over_tgt;
+      [&](int k, double out) {
+        obuf[stage_slot(lane, k)] = out;
         if ((k + 1) % CH == 0 || k + 1 == NLEV) {
-          // flush the finished chunk of this column group: its gact lanes store gact rows x CH levels
+          // flush the finished chunk of this column group: its gact lanes store gact rows x CH levels. The quotient
+          // by the target thickness is taken here, by whichever lane stores the value: states leave as x / tgt
+          // (ComputeIntrinsicsTag :294-307), tracers as Qdp = x and Q = x / tgt (update_q)
           const int chunk = k / CH;
           __syncwarp(gmask);
 #pragma unroll
@@ -377,9 +383,11 @@ __global__ void __launch_bounds__(REMAP_MAX_WARPS * 32) remap_kernel(const Remap
             const int e = i * gact + grank, rowl = e / CH, lev = e % CH, level = chunk * CH + lev;
             const int row = gfirst + rowl;
             if (level < NLEV) {
-              ptab[row][level] = obuf[row * RS + lev];
+              const double x = obuf[stage_slot(row, lev)];
+              const double t = div_rcp(x, c.tgt[level], c.rtgt[level]);
               double* qp = qtab[row];
-              if (qp) qp[level] = qbuf[row * RS + lev];
+              if (qp) { ptab[row][level] = x; qp[level] = t; }
+              else ptab[row][level] = t;
             }
           }
           __syncwarp(gmask);
@@ -432,7 +440,7 @@ __global__ void __launch_bounds__(64) remap_eulerian_kernel(const RemapArgs a, c
     double* fld = a.qdp + off_q(ie, a.np1_qdp, q) + p * NLEV;
     double* Qf = a.Q + (((size_t)ie * QSIZE_D + q) * NPSQ + p) * NLEV;
     ppm_sweep(c, a.alg, true, false, [](int) {}, [&](int k) { return fld[k]; },
-              [&](int k, double x, double over_tgt) { fld[k] = x; Qf[k] = over_tgt; });
+              [&](int k, double x) { fld[k] = x; Qf[k] = div_rcp(x, c.tgt[k], c.rtgt[k]); });
   }
 }
 
@@ -490,7 +498,7 @@ __global__ void __launch_bounds__(64)
   for (int f = threadIdx.x; f < nfields; f += blockDim.x) {
     double* fld = fields + ((size_t)f * ncols + col) * NLEV;
     ppm_sweep(c, alg, true, false, [](int) {}, [&](int k) { return fld[k]; },
-              [&](int k, double x, double) { fld[k] = x; });
+              [&](int k, double x) { fld[k] = x; });
   }
 }
 
