@@ -16,6 +16,8 @@
 #include <string>
 
 #include "CaarFunctor.hpp"
+#include "CamForcing.hpp"
+#include "Diagnostics.hpp"
 #include "Context.hpp"
 #include "Elements.hpp"
 #include "EulerStepFunctor.hpp"
@@ -120,6 +122,20 @@ void hxx_vertical_remap(int np1, int np1_qdp, double dt) {
   Context::singleton().get_vertical_remap_manager().run_remap(np1, np1_qdp, dt);
 }
 void hxx_update_q(int np1_qdp, int np1) { Homme::update_q(np1_qdp, np1); }
+// apply_cam_forcing / apply_cam_forcing_dynamics (CamForcing.cpp:149-174) the way prim_run_subcycle_c calls them
+// (prim_driver.cpp:66-82): tracer time levels from nstep first, then the pass the namelist's ftype selects
+void hxx_apply_forcing(double dt) {
+  SimulationParams& params = Context::singleton().get_simulation_params();
+  Context::singleton().get_time_level().update_tracers_levels(params.qsplit);
+  if (params.ftype == ForcingAlg::FORCING_DEBUG) Homme::apply_cam_forcing(dt);
+  else if (params.ftype == ForcingAlg::FORCING_2) Homme::apply_cam_forcing_dynamics(dt);
+}
+// Diagnostics::prim_diag_scalars + prim_energy_halftimes (Diagnostics.cpp:37-185) into the registered F90 arrays
+void hxx_diagnostics(int before_advance, int ivar_scalars, int ivar_energy) {
+  Diagnostics& d = Context::singleton().get_diagnostics();
+  d.prim_diag_scalars(before_advance != 0, ivar_scalars);
+  d.prim_energy_halftimes(before_advance != 0, ivar_energy);
+}
 // One element-local operator of SphereOperators.hpp on caller-provided [np][np][nlev] fields of element `ie`
 // (a team per element as in the functors; only the team of `ie` works). Returns silently on an unknown name.
 void hxx_sphere_op(const char* op, int ie, const double* in, double* out, double nu_ratio) {

@@ -12,9 +12,12 @@ derived_vn0, eta_dot_dpdn, omega_p, phi, dpdiss_*, divdp, divdp_proj, qtens_biha
 import numpy as np
 import pytest
 
-from functor_pair import Pair
+from functor_pair import FIELDS, Pair
 from hommexx_b200 import homme
 from oracle import oraclelib
+
+FIELDS_WITH_FORCING = {0: FIELDS + ["fm", "ft", "fq"], 2: FIELDS + ["fm", "ft"]}
+
 
 @pytest.fixture(scope="class")
 def ne4():
@@ -124,5 +127,44 @@ def test_every_functor_in_the_option_variants(case):
         p.call("hxx_vertical_remap", 2, 1, dtq * max(cfg.rsplit, 1))
         p.call("hxx_update_q", 1, 2)
         p.same(case + " remap + update_q", changed=("qdp",))
+    finally:
+        p.close()
+
+
+# ---- CamForcing.cpp and Diagnostics.cpp, one call at a time ---------------------------------------------------------
+@pytest.mark.parametrize("moist,ftype", [(0, 0), (1, 0), (0, 2)])
+def test_cam_forcing_pass(moist, ftype):
+    """apply_cam_forcing (ftype 0: states and tracers, the negativity clamp, the moist ps_v / dp3d update) and
+    apply_cam_forcing_dynamics (ftype 2) on point-wise random tendencies pushed with f90_push_forcing_to_cxx."""
+    from forcing_inputs import fill_forcing
+    cfg = homme.preset("ne4", moisture=moist, ftype=ftype)
+    p = Pair(cfg, oraclelib.ORACLE_LIB, b"cpu-oracle", fields=FIELDS_WITH_FORCING[ftype])
+    try:
+        p.ho.run_subcycle()                      # both at the same time levels (Pair warmed the reference only)
+        p.reset()
+        for h in (p.hr, p.ho):
+            fill_forcing(h)
+            h.push_forcing()
+        p.call("hxx_apply_forcing", cfg.tstep * cfg.rsplit)
+        p.same(f"apply_cam_forcing moist={moist} ftype={ftype}", changed=("v", "t") + (("qdp",) if ftype == 0 else ()))
+    finally:
+        p.close()
+
+
+def test_diagnostics_calls():
+    """prim_diag_scalars + prim_energy_halftimes into the F90 accumulators, before and after an advance."""
+    cfg = homme.preset("ne4", disable_diagnostics=0, state_frequency=9999, moisture=1, use_cpstar=1)
+    p = Pair(cfg, oraclelib.ORACLE_LIB, b"cpu-oracle")
+    try:
+        p.ho.run_subcycle()
+        p.reset()
+        for (before, ivs, ive) in [(1, 3, 2), (1, 0, 0), (0, 1, 1)]:
+            p.call("hxx_diagnostics", before, ivs, ive)
+            a, b = p.hr.accum(), p.ho.accum()
+            for k in a:
+                assert np.isfinite(a[k]).all(), k
+                assert np.array_equal(a[k], b[k]), ((before, ivs, ive), k, float(np.abs(a[k] - b[k]).max()))
+        assert np.abs(a["KEner"]).max() > 0 and np.abs(a["IEner"]).max() > 0 and np.abs(a["Qmass"]).max() > 0
+        p.same("diagnostics leave the state alone")
     finally:
         p.close()
