@@ -106,3 +106,14 @@ def test_reference_timing_build_agrees_with_its_serial_build():
     for k in ("v", "T", "dp3d", "ps_v", "Qdp", "Q"):
         err = np.sqrt(((a[k] - b[k]) ** 2).sum()) / np.sqrt((b[k] ** 2).sum())
         assert err <= 1e-11, (k, err)
+
+
+def test_long_run_stays_bit_identical():
+    """120 dynamics steps (30 calls) of the moist, limiter-9, qsplit 2 / rsplit 2 variant: two and a half simulated hours
+    past the ten-step cases, through many more limiter iterations and remap configurations, still bit for bit."""
+    cfg = homme.preset("prtcA", moisture=1, qsplit=2, rsplit=2, limiter_option=9)
+    ref = run(cfg, reference_lib(cfg.nlev, cfg.qsize_d), 120)
+    ora = run(cfg, oraclelib.ORACLE_LIB, 120)
+    assert np.array_equal(ref["_tl"], ora["_tl"]) and ref["_tl"][0] == 120
+    for k in PROGNOSTIC:
+        assert np.array_equal(ref[k], ora[k]), (k, float(np.abs(ref[k] - ora[k]).max()))
