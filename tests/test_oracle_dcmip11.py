@@ -42,3 +42,24 @@ def test_one_day_of_deformational_flow():
     assert np.abs(ps - 1e5).max() < 20.0                                # the flow is non-divergent in the column
     # and it really deforms the fields: a day moves the bells by 30 degrees and stretches them
     assert np.abs(q[0] - q0[0]).max() > 0.3
+
+
+def test_dcmip11_on_the_reference_functors_matches_the_oracle():
+    """The same tracer-only driver on the REFERENCE's own build: its prim_run_subcycle_c refuses prescribed winds, but
+    its functors' run methods (EulerStepFunctor::euler_step x 3, qdp_time_avg, VerticalRemapManager::run_remap,
+    update_q — bound to the section-C hooks by oracle/ref_hommexx_api.cpp) advect the DCMIP 1-1 tracers through the
+    analytic deformational flow all the same. 24 steps at ne8: every tracer array bit-identical to the oracle."""
+    from reference_lib import reference_lib
+    runs = []
+    for lib in (reference_lib(26, 4), oraclelib.ORACLE_LIB):
+        d = dcmip.Dcmip11(8, 26, lib, tstep=600.0)
+        m0 = d.masses()
+        for _ in range(24):
+            d.step()
+        runs.append((d.q(), d.masses() / m0, d.h.get_field("qdp"), d.h.get_field("Q"), d.h.get_field("dp3d")))
+        d.close()
+    (qr, mr, qdpr, Qr, dpr), (qo, mo, qdpo, Qo, dpo) = runs
+    assert np.isfinite(qr).all() and np.abs(mr - 1.0).max() <= 1e-13
+    assert np.abs(qr[0] - qr[0].mean()).max() > 0.1                      # a non-trivial field
+    for a, b, nm in ((qr, qo, "q"), (mr, mo, "mass"), (qdpr, qdpo, "qdp"), (Qr, Qo, "Q"), (dpr, dpo, "dp3d")):
+        assert np.array_equal(a, b), (nm, float(np.abs(a - b).max()))
